@@ -1,0 +1,297 @@
+// Dense projection Y[M,N] = X[M,K] * W[N,K]^T for the decoder's QKV / O / gate_up / down / lm_head
+// linears (reference operator: F.linear in $VLLM/model_executor/layers/utils.py:92-98, which
+// dispatches to cuBLASLt).  Hand-written for sm_100a:
+//
+//   * operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a ring of shared
+//     memory stages guarded by full/empty mbarriers;
+//   * one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator
+//     in tensor memory, double-buffered so the epilogue of tile i overlaps the main loop of i+1;
+//   * four epilogue warps read the accumulator back with tcgen05.ld and store bf16 (or fp32
+//     split-K partials) straight to global memory;
+//   * the kernel is persistent: grid = #SMs, tiles are walked with a grouped raster so that a
+//     wave shares activation tiles through L2.
+//
+// Orientation ("swap-AB"): the WEIGHT tile is the MMA's M operand (128 weight rows = 128 TMEM
+// lanes) and the ACTIVATION tile is the N operand (BLOCK_X tokens = BLOCK_X fp32 TMEM columns).
+// A decode step with M = 1..256 tokens is therefore ONE tile column: every weight byte is read
+// from HBM exactly once and no tensor-core work is spent on padding rows; a prefill step uses
+// 128 x 256 tiles.  Weight streaming is the roofline for decode (HBM), the tensor pipe for prefill.
+#include "common.cuh"
+#include "runtime.h"
+#include "../../include/b200.h"
+
+namespace b200 {
+
+constexpr int kBlockW = 128;  // weight rows per tile  (UMMA M)
+constexpr int kBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;  // warp0 TMA, warp1 MMA+TMEM alloc, warps 2-5 epilogue
+
+template <int BLOCK_X>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockW * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_X * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  // as many stages as fit in ~200 KB: deep rings keep >100 KB of weight loads in flight per SM,
+  // which is what an HBM-bound decode tile needs (latency x per-SM share of 6.5 TB/s).
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 12 ? 12 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_X < 32 ? 32 : 2 * BLOCK_X;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+  // Bounded wait: a protocol bug becomes a trapped kernel (reported as a CUDA error) instead of
+  // a hung GPU.  globaltimer is only consulted every 4096 failed probes.
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
+struct TileCoord {
+  int split, m_tile, n_tile;
+};
+
+// Grouped raster: tiles are ordered (m-group, n, m-in-group, split) so that concurrently running
+// CTAs share a handful of activation tiles and each weight tile is pulled from HBM once per group.
+__device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles, int splits,
+                                                 int group_m) {
+  TileCoord c;
+  c.split = u % splits;
+  int t = u / splits;
+  const int per_group = group_m * n_tiles;
+  const int g = t / per_group;
+  const int first_m = g * group_m;
+  const int gm = min(group_m, m_tiles - first_m);
+  const int r = t - g * per_group;
+  c.n_tile = r / gm;
+  c.m_tile = first_m + r % gm;
+  return c;
+}
+
+template <int BLOCK_X>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
+                         int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
+                         int m_tiles, int group_m) {
+  using Cfg = GemmCfg<BLOCK_X>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kb_per_split = (K / kBlockK) / splits;
+  const int total_units = n_tiles * m_tiles * splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const uint64_t hint_w = (m_tiles > 1) ? kEvictNormal : kEvictFirst;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const TileCoord c = decode_unit(u, n_tiles, m_tiles, splits, group_m);
+        const int k0 = c.split * kb_per_split * kBlockK;
+        for (int kb = 0; kb < kb_per_split; ++kb) {
+          mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+          uint8_t* a = smem + stage * Cfg::kStageBytes;
+          uint8_t* b = a + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(a, &tmap_w, &full_bar[stage], k0 + kb * kBlockK, c.n_tile * kBlockW, hint_w);
+          tma_load_2d(b, &tmap_x, &full_bar[stage], k0 + kb * kBlockK, c.m_tile * BLOCK_X,
+                      kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockW, BLOCK_X);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        mbar_wait_guarded(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_X);
+        for (int kb = 0; kb < kb_per_split; ++kb) {
+          mbar_wait_guarded(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                      umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bf16* Yb = reinterpret_cast<bf16*>(Yv);
+    float* Yf = reinterpret_cast<float*>(Yv);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const TileCoord c = decode_unit(u, n_tiles, m_tiles, splits, group_m);
+      mbar_wait_guarded(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int n = c.n_tile * kBlockW + quad * 32 + lane;
+      const int m_base = c.m_tile * BLOCK_X;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
+      const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
+      constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_X; c0 += CH) {
+        if (m_base + c0 >= M) break;  // warp-uniform: rest of the tile is padding
+        uint32_t r[CH];
+        if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, r);
+        else tmem_ld_32x16(t_addr + c0, r);
+        tmem_ld_wait();
+        if (n < N) {
+          if (out_f32) {
+            float* dst = Yf + split_off + (size_t)(m_base + c0) * ldy + n;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __uint_as_float(r[j]);
+          } else {
+            bf16* dst = Yb + (size_t)(m_base + c0) * ldy + n;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_X>
+static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                       int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_X>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_X>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      b200_set_error("gemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
+                     cudaGetErrorString(e));
+      return B200_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_tmap_bf16_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBlockW, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X, kBlockK);
+  if (rc) return rc;
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
+  const int total = n_tiles * m_tiles * splits;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int grid = total < sms ? total : sms;
+  const int group_m = m_tiles < 8 ? m_tiles : 8;
+  gemm_bf16_tcgen05_kernel<BLOCK_X><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
+      tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
+  return b200_check_launch("b200_gemm_bf16");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm_suggest_splits(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0 || K % kBlockK) return 1;
+  if (M > 256) return 1;  // prefill: tensor-bound, plenty of tiles
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int kb = K / kBlockK;
+  int splits = 1;
+  // HBM-bound decode: want >= ~1 CTA per SM streaming weights, but keep >= 8 k-blocks per split
+  while (n_tiles * splits * 2 <= sms && splits < 8 && kb % (splits * 2) == 0 &&
+         kb / (splits * 2) >= 8)
+    splits *= 2;
+  return splits;
+}
+
+extern "C" int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K,
+                              int64_t ldx, int64_t ldw, int64_t ldy, int out_f32, int splits,
+                              void* stream) {
+  B200_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(K % kBlockK == 0, "gemm: K=%d must be a multiple of %d", K, kBlockK);
+  B200_REQUIRE(splits >= 1 && (K / kBlockK) % splits == 0,
+               "gemm: splits=%d must divide K/%d=%d", splits, kBlockK, K / kBlockK);
+  B200_REQUIRE(splits == 1 || out_f32, "gemm: split-K output must be fp32 partials");
+  B200_REQUIRE(ldx >= K && ldw >= K && ldy >= N, "gemm: leading dimensions too small");
+  if (M == 0) return B200_OK;
+  const DeviceInfo& d = device_info();
+  if (!d.valid || d.cc_major != 10) {
+    b200_set_error("gemm: tcgen05 kernel needs an sm_100 device (found cc %d.%d)", d.cc_major,
+                   d.cc_minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M <= 16) return launch_gemm<16>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+  if (M <= 32) return launch_gemm<32>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+  if (M <= 64) return launch_gemm<64>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+  if (M <= 128) return launch_gemm<128>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+  return launch_gemm<256>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+}

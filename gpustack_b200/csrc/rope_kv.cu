@@ -1,0 +1,89 @@
+// Neox-style rotary embedding on q/k (in place) fused with the paged KV-cache scatter.
+// Reference operators: $VLLM/model_executor/layers/rotary_embedding/base.py:150-215 (rotation,
+// cos|sin cache in the model dtype) and $VLLM/_custom_ops.py:2591-2610 (reshape_and_cache_flash).
+// One CTA per token; each work item is a 16-byte vector (8 bf16).  Rotation is done in fp32 and
+// rounded once (the reference rounds every bf16 op; the difference is < 2 bf16 ulp).
+#include "common.cuh"
+#include "../../include/b200.h"
+
+namespace b200 {
+
+__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
+  f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
+  f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256)
+rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positions,
+                     const bf16* __restrict__ cos_sin, bf16* __restrict__ k_cache,
+                     bf16* __restrict__ v_cache, const int32_t* __restrict__ slot_mapping, int Hq,
+                     int Hkv, int D, int block_size) {
+  const int t = blockIdx.x;
+  const int half = D >> 1;
+  const int vec_per_half = half >> 3;           // 16-byte vectors in half a head
+  const int rope_items = (Hq + Hkv) * vec_per_half;
+  const int v_items = Hkv * (D >> 3);
+  const int pos = positions[t];
+  const int slot = slot_mapping[t];
+  const size_t row = (size_t)t * (size_t)(Hq + 2 * Hkv) * D;
+  const bf16* cs = cos_sin + (size_t)pos * D;
+  const int blk = slot >= 0 ? slot / block_size : 0;
+  const int off = slot >= 0 ? slot % block_size : 0;
+
+  for (int it = threadIdx.x; it < rope_items + v_items; it += blockDim.x) {
+    if (it < rope_items) {
+      const int head = it / vec_per_half;       // 0..Hq-1 = q heads, then k heads
+      const int vi = it % vec_per_half;
+      bf16* p1 = qkv + row + (size_t)head * D + vi * 8;
+      bf16* p2 = p1 + half;
+      float x1[8], x2[8], c[8], s[8], o1[8], o2[8];
+      unpack8(ld_v4(p1), x1);
+      unpack8(ld_v4(p2), x2);
+      unpack8(ld_v4(cs + vi * 8), c);
+      unpack8(ld_v4(cs + half + vi * 8), s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o1[j] = x1[j] * c[j] - x2[j] * s[j];
+        o2[j] = x2[j] * c[j] + x1[j] * s[j];
+      }
+      const uint4 r1 = pack8(o1), r2 = pack8(o2);
+      st_v4(p1, r1);
+      st_v4(p2, r2);
+      if (head >= Hq && slot >= 0) {
+        const int kh = head - Hq;
+        bf16* kc = k_cache + (((size_t)blk * Hkv + kh) * block_size + off) * D + vi * 8;
+        st_v4(kc, r1);
+        st_v4(kc + half, r2);
+      }
+    } else if (slot >= 0) {
+      const int j = it - rope_items;
+      const int vh = j / (D >> 3);
+      const int vi = j % (D >> 3);
+      const bf16* src = qkv + row + (size_t)(Hq + Hkv + vh) * D + vi * 8;
+      bf16* dst = v_cache + (((size_t)blk * Hkv + vh) * block_size + off) * D + vi * 8;
+      st_v4(dst, ld_v4(src));
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin,
+                                  void* k_cache, void* v_cache, const int32_t* slot_mapping, int T,
+                                  int Hq, int Hkv, int D, int block_size, void* stream) {
+  B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "rope_kv_write: bad shape");
+  B200_REQUIRE(D % 16 == 0 && D <= 256, "rope_kv_write: head_dim %d must be a multiple of 16", D);
+  if (T == 0) return B200_OK;
+  rope_kv_write_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(
+      (bf16*)qkv, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache, slot_mapping,
+      Hq, Hkv, D, block_size);
+  return b200_check_launch("b200_rope_kv_write");
+}

@@ -1,0 +1,198 @@
+"""Operator wrappers: torch CUDA tensors in, libb200.so kernels on torch's current stream.
+
+Each function mirrors one entry point of include/b200.h (and through it one operator of the
+reference's vLLM backend).  torch is used for memory and streams only; there is deliberately no
+eager/PyTorch fallback -- a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from .lib import B200Error, check, load
+
+BLOCK_SIZE = 16  # tokens per KV page (vLLM default block_size)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise B200Error(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise B200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B200Error(f"{name}: tensor must be contiguous")
+
+
+def device_info() -> dict:
+    lib = load()
+    v = [C.c_int() for _ in range(4)]
+    check(lib.b200_device_info(*[C.byref(x) for x in v]), "device_info")
+    return {"sm_count": v[0].value, "cc": (v[1].value, v[2].value), "l2_bytes": v[3].value}
+
+
+# ------------------------------------------------------------------------------ normalisation
+def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None):
+    _req(x, torch.bfloat16, "x"); _req(w, torch.bfloat16, "w")
+    T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    check(load().b200_rms_norm(_p(x), _p(w), _p(y), T, H, eps, _stream()), "rms_norm")
+    return y
+
+
+def fused_add_rms_norm(x, residual, w, eps, out=None, residual_out=None):
+    """returns (y, residual_out); pass out=x, residual_out=residual for the in-place form."""
+    _req(x, torch.bfloat16, "x"); _req(residual, torch.bfloat16, "residual"); _req(w, torch.bfloat16, "w")
+    T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    r = torch.empty_like(x) if residual_out is None else residual_out
+    check(load().b200_fused_add_rms_norm(_p(x), _p(residual), _p(w), _p(y), _p(r), T, H, eps, _stream()),
+          "fused_add_rms_norm")
+    return y, r
+
+
+def fused_add_rms_norm_partials(partials, residual, w, eps, out, residual_out):
+    _req(partials, torch.float32, "partials"); _req(w, torch.bfloat16, "w")
+    S, T, H = partials.shape
+    check(load().b200_fused_add_rms_norm_partials(_p(partials), S, _p(residual), _p(w), _p(out),
+                                                  _p(residual_out), T, H, eps, _stream()),
+          "fused_add_rms_norm_partials")
+    return out, residual_out
+
+
+# ------------------------------------------------------------------- rope + kv-cache scatter
+def rope_kv_write(qkv, positions, cos_sin, k_cache, v_cache, slot_mapping, Hq, Hkv, D):
+    _req(qkv, torch.bfloat16, "qkv"); _req(positions, torch.int32, "positions")
+    _req(cos_sin, torch.bfloat16, "cos_sin"); _req(slot_mapping, torch.int32, "slot_mapping")
+    _req(k_cache, torch.bfloat16, "k_cache"); _req(v_cache, torch.bfloat16, "v_cache")
+    T = qkv.shape[0]
+    if qkv.shape[1] != (Hq + 2 * Hkv) * D:
+        raise B200Error("rope_kv_write: qkv width mismatch")
+    check(load().b200_rope_kv_write(_p(qkv), _p(positions), _p(cos_sin), _p(k_cache), _p(v_cache),
+                                    _p(slot_mapping), T, Hq, Hkv, D, k_cache.shape[2], _stream()),
+          "rope_kv_write")
+
+
+def silu_and_mul(x, out=None):
+    _req(x, torch.bfloat16, "x")
+    T, I2 = x.shape
+    y = torch.empty((T, I2 // 2), dtype=x.dtype, device=x.device) if out is None else out
+    check(load().b200_silu_and_mul(_p(x), _p(y), T, I2 // 2, _stream()), "silu_and_mul")
+    return y
+
+
+def embedding(ids, table, out=None, vocab_start=0, vocab_end=None):
+    _req(ids, torch.int32, "ids"); _req(table, torch.bfloat16, "table")
+    T, H = ids.shape[0], table.shape[1]
+    y = torch.empty((T, H), dtype=table.dtype, device=table.device) if out is None else out
+    ve = vocab_start + table.shape[0] if vocab_end is None else vocab_end
+    check(load().b200_embedding(_p(ids), _p(table), _p(y), T, H, vocab_start, ve, _stream()), "embedding")
+    return y
+
+
+def argmax(logits, out_idx=None, out_val=None):
+    _req(logits, torch.float32, "logits")
+    B, V = logits.shape
+    idx = torch.empty((B,), dtype=torch.int32, device=logits.device) if out_idx is None else out_idx
+    check(load().b200_argmax_f32(_p(logits), logits.stride(0), _p(idx), _p(out_val), B, V, _stream()),
+          "argmax")
+    return idx
+
+
+def gather_rows(x, rows, out=None):
+    _req(x, torch.bfloat16, "x"); _req(rows, torch.int32, "rows")
+    n, H = rows.shape[0], x.shape[1]
+    y = torch.empty((n, H), dtype=x.dtype, device=x.device) if out is None else out
+    check(load().b200_gather_rows(_p(x), _p(rows), _p(y), n, H, _stream()), "gather_rows")
+    return y
+
+
+# --------------------------------------------------------------------------------------- GEMM
+def gemm_suggest_splits(M: int, N: int, K: int) -> int:
+    return load().b200_gemm_suggest_splits(M, N, K)
+
+
+def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1):
+    """y = x @ w.T (x [M,K], w [N,K], bf16).  splits>1 returns fp32 partials [splits, M, N]."""
+    if not (x.is_cuda and w.is_cuda) or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise B200Error("gemm: bf16 CUDA tensors required")
+    if x.stride(-1) != 1 or w.stride(-1) != 1:
+        raise B200Error("gemm: K must be the contiguous dimension")
+    M, K = x.shape
+    N = w.shape[0]
+    out_f32 = 1 if (out_dtype == torch.float32 or splits > 1) else 0
+    if out is None:
+        shape = (splits, M, N) if splits > 1 else (M, N)
+        out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    ldy = out.stride(-2)
+    check(load().b200_gemm_bf16(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), ldy, out_f32,
+                                splits, _stream()), "gemm")
+    return out
+
+
+def splitk_reduce(partials, out=None):
+    _req(partials, torch.float32, "partials")
+    S, M, N = partials.shape
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=partials.device) if out is None else out
+    check(load().b200_splitk_reduce(_p(partials), S, _p(y), M, N, y.stride(0), _stream()), "splitk_reduce")
+    return y
+
+
+# ---------------------------------------------------------------------------------- attention
+def attn_decode_splits(B, Hkv, max_seq_len) -> int:
+    return load().b200_attn_decode_splits(B, Hkv, max_seq_len, BLOCK_SIZE)
+
+
+def attn_decode_workspace(B, Hq, D, num_splits, device) -> torch.Tensor:
+    n = load().b200_attn_decode_workspace_bytes(B, Hq, D, num_splits)
+    return torch.empty((n + 3) // 4, dtype=torch.float32, device=device)
+
+
+def paged_attn_decode(q, q_stride, k_cache, v_cache, block_table, seq_lens, out, Hq, Hkv, D, scale,
+                      num_splits=1, workspace=None):
+    """q: [B, >=Hq*D] view into the qkv buffer (row stride q_stride elements)."""
+    B = seq_lens.shape[0]
+    _req(block_table, torch.int32, "block_table"); _req(seq_lens, torch.int32, "seq_lens")
+    check(load().b200_paged_attn_decode(_p(q), q_stride, _p(k_cache), _p(v_cache), _p(block_table),
+                                        block_table.shape[1], _p(seq_lens), _p(out), _p(workspace),
+                                        num_splits, B, Hq, Hkv, D, k_cache.shape[2], scale, _stream()),
+          "paged_attn_decode")
+    return out
+
+
+def attn_prefill_tile(Hq, Hkv) -> int:
+    t = load().b200_attn_prefill_tile(Hq, Hkv)
+    if t <= 0:
+        raise B200Error(f"prefill attention: unsupported head grouping {Hq}/{Hkv}")
+    return t
+
+
+def build_prefill_tiles(q_lens: Sequence[int], tile: int):
+    """Host-side tile list for b200_paged_attn_prefill: (tile_seq, tile_q0) int32 lists."""
+    seqs, q0s = [], []
+    for s, n in enumerate(q_lens):
+        for q0 in range(0, n, tile):
+            seqs.append(s)
+            q0s.append(q0)
+    return seqs, q0s
+
+
+def paged_attn_prefill(q, q_stride, k_cache, v_cache, block_table, cu_q, ctx_lens, tile_seq, tile_q0,
+                       out, Hq, Hkv, D, scale):
+    for t, n in ((block_table, "block_table"), (cu_q, "cu_q"), (ctx_lens, "ctx_lens"),
+                 (tile_seq, "tile_seq"), (tile_q0, "tile_q0")):
+        _req(t, torch.int32, n)
+    check(load().b200_paged_attn_prefill(_p(q), q_stride, _p(k_cache), _p(v_cache), _p(block_table),
+                                         block_table.shape[1], _p(cu_q), _p(ctx_lens), _p(tile_seq),
+                                         _p(tile_q0), tile_seq.shape[0], _p(out), Hq, Hkv, D,
+                                         k_cache.shape[2], scale, _stream()), "paged_attn_prefill")
+    return out

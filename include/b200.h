@@ -1,0 +1,135 @@
+/*
+ * b200.h — C ABI of libb200.so, the sm_100a kernel library behind the engine.
+ *
+ * GPUStack has no in-process engine ABI: its engine boundary is process + CLI + HTTP
+ * (reference: gpustack/worker/backends/custom.py:141-159, gpustack/worker/serve_manager.py:1000-1048,
+ * gpustack/routes/openai.py:92-181).  That boundary is implemented by gpustack_b200/{cli,server}.py.
+ * This header is the INTERNAL boundary the north star asks for ("Python over PyTorch tensors
+ * calling the kernels through a thin C-ABI extension"): one entry point per operator on the
+ * decoder hot path, each citing the operator of the reference's vLLM backend it replaces
+ * ($VLLM = site-packages/vllm 0.22.0, the engine gpustack/worker/backends/vllm.py:403-407 launches).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory;
+ *   - kernels never allocate and never synchronise; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, negative on error (B200_ERR_*), message via b200_last_error();
+ *   - bf16 tensors are row-major, innermost dimension contiguous, 16-byte aligned rows.
+ */
+#ifndef B200_H_
+#define B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+#define B200_ERR_INVALID (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int b200_abi_version(void);
+const char* b200_last_error(void);
+/* sm count, compute capability and L2 size of the current device. */
+int b200_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
+
+/* ---- normalisation: $VLLM/model_executor/layers/layernorm.py:104-150,
+ *      math $VLLM/ir/ops/layernorm.py:10-58 ------------------------------------------------- */
+/* y = bf16(bf16(x * rsqrt(mean(x^2) + eps)) * w); x,y [T,H] bf16, w [H] bf16. */
+int b200_rms_norm(const void* x, const void* w, void* y, int T, int H, float eps, void* stream);
+/* z = x + residual (fp32); residual_out = bf16(z); y = rmsnorm(z) as above.
+ * y may alias x, residual_out may alias residual (the reference op is in-place). */
+int b200_fused_add_rms_norm(const void* x, const void* residual, const void* w, void* y,
+                            void* residual_out, int T, int H, float eps, void* stream);
+/* Same, but x arrives as `splits` fp32 partial sums [splits][T][H] (split-K GEMM output);
+ * the partials are summed in fp32 before the residual add.  residual may be NULL (first layer). */
+int b200_fused_add_rms_norm_partials(const float* partials, int splits, const void* residual,
+                                     const void* w, void* y, void* residual_out, int T, int H,
+                                     float eps, void* stream);
+
+/* ---- rotary embedding + KV-cache write:
+ *      $VLLM/model_executor/layers/rotary_embedding/base.py:150-215 (neox style) and
+ *      $VLLM/_custom_ops.py:2591-2610 (reshape_and_cache_flash) -------------------------------- */
+/* qkv [T, (Hq+2*Hkv)*D] bf16: q and k heads are rotated in place; rotated k and v are scattered
+ * into k_cache/v_cache laid out [num_blocks][Hkv][block_size][D] at slot_mapping[t]
+ * (= block*block_size + offset; negative = skip).  cos_sin [max_pos][D] bf16 = cos | sin halves. */
+int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin, void* k_cache,
+                       void* v_cache, const int32_t* slot_mapping, int T, int Hq, int Hkv, int D,
+                       int block_size, void* stream);
+
+/* ---- activation: $VLLM/model_executor/layers/activation.py:133-143 ----------------------- */
+/* out[t, i] = bf16(bf16(silu(x[t, i])) * x[t, I + i]);  x [T, 2I] bf16, out [T, I] bf16. */
+int b200_silu_and_mul(const void* x, void* out, int T, int I, void* stream);
+
+/* ---- embedding + greedy sampler:
+ *      $VLLM/model_executor/layers/vocab_parallel_embedding.py, $VLLM/v1/sample/sampler.py -- */
+/* out[t] = table[ids[t] - vocab_start] if vocab_start <= ids[t] < vocab_end else 0. */
+int b200_embedding(const int32_t* ids, const void* table, void* out, int T, int H, int vocab_start,
+                   int vocab_end, void* stream);
+/* out_idx[b] = lowest index of the row maximum of logits[b, :V] (fp32, row stride ld);
+ * out_val[b] (optional) = that maximum. */
+int b200_argmax_f32(const float* logits, int64_t ld, int32_t* out_idx, float* out_val, int B, int V,
+                    void* stream);
+/* gather rows: out[i] = x[rows[i]]; x [*,H] bf16 (used to pick each sequence's last token). */
+int b200_gather_rows(const void* x, const int32_t* rows, void* out, int n, int H, void* stream);
+
+/* ---- dense projection (tcgen05/TMEM, TMA-fed):
+ *      $VLLM/model_executor/layers/utils.py:92-98 (F.linear of QKV/O/gate_up/down/lm_head) ---- */
+/* Y[M,N] = X[M,K] * W[N,K]^T.  X,W bf16 (K contiguous, ldx/ldw in elements), fp32 accumulate.
+ *   out_f32 == 0: Y bf16 [M, ldy];  out_f32 == 1: Y fp32 [M, ldy].
+ *   splits > 1 : K is cut into `splits` equal ranges and Y must be fp32 [splits][M][ldy]
+ *                partial sums (reduced by b200_fused_add_rms_norm_partials / b200_splitk_reduce).
+ * K % 64 == 0 required.  M, N arbitrary (tails are zero-filled by TMA and masked on store). */
+int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                   int64_t ldw, int64_t ldy, int out_f32, int splits, void* stream);
+/* Y[m,n] = bf16(sum_s partials[s][m][n]). */
+int b200_splitk_reduce(const float* partials, int splits, void* Y, int M, int N, int64_t ldy,
+                       void* stream);
+/* Heuristic used by the engine: how many K-splits b200_gemm_bf16 should use for this shape. */
+int b200_gemm_suggest_splits(int M, int N, int K);
+
+/* ---- paged-KV attention: $VLLM/v1/attention/backends/flashinfer.py:1095-1230 -------------- */
+/* Decode: one query token per sequence.  q [B, Hq, D] bf16 with row stride q_stride (elements),
+ * out [B, Hq*D] bf16, block_table [B, max_blocks] int32, seq_lens [B] int32 (incl. the new
+ * token).  workspace: fp32 scratch of b200_attn_decode_workspace_bytes(); num_splits from
+ * b200_attn_decode_splits() or caller-chosen (>=1). */
+int b200_attn_decode_splits(int B, int Hkv, int max_seq_len, int block_size);
+size_t b200_attn_decode_workspace_bytes(int B, int Hq, int D, int num_splits);
+int b200_paged_attn_decode(const void* q, int64_t q_stride, const void* k_cache,
+                           const void* v_cache, const int32_t* block_table, int max_blocks,
+                           const int32_t* seq_lens, void* out, void* workspace, int num_splits,
+                           int B, int Hq, int Hkv, int D, int block_size, float scale,
+                           void* stream);
+/* Prefill / chunked prefill: ragged batch of query chunks.  Sequence s contributes tokens
+ * [cu_q[s], cu_q[s+1]) of q; its chunk starts at context position ctx_lens[s] (tokens already in
+ * the cache) and attends causally to cache positions [0, ctx_lens[s] + i].  K/V of the chunk must
+ * already be in the cache (b200_rope_kv_write runs first).  tile_seq/tile_q0 [num_tiles] list the
+ * (sequence, first query offset) of each 32-token query tile, built on the host. */
+int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache,
+                            const void* v_cache, const int32_t* block_table, int max_blocks,
+                            const int32_t* cu_q, const int32_t* ctx_lens, const int32_t* tile_seq,
+                            const int32_t* tile_q0, int num_tiles, void* out, int Hq, int Hkv, int D,
+                            int block_size, float scale, void* stream);
+
+/* ---- tensor-parallel all-reduce over NVLink peer memory:
+ *      $VLLM/distributed/device_communicators/cuda_communicator.py:241-290 (custom all-reduce) */
+int b200_ipc_get_handle(void* dev_ptr, void* handle_out_host /* 64 bytes */);
+int b200_ipc_open_handle(const void* handle_host /* 64 bytes */, void** dev_ptr_out);
+int b200_ipc_close_handle(void* dev_ptr);
+/* One-shot all-reduce(sum) of bf16 [n] fused with residual add + RMSNorm of the reduced rows:
+ * peers[r] = rank r's staging buffer (bf16 [n], already filled by that rank's GEMM);
+ * flags[r] = rank r's flag words (peer-mapped, >= 2*world uint32, zero-initialised once).
+ * Every rank reduces all rows (redundantly) so no second exchange is needed.
+ * w == NULL: plain all-reduce into y.  epoch must increase by 1 on every call. */
+int b200_allreduce_add_rms_norm(void* const* peers_host, void* const* flags_host, int world,
+                                int rank, uint32_t epoch, const void* residual, const void* w,
+                                void* y, void* residual_out, int T, int H, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_H_ */

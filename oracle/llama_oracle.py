@@ -1,0 +1,236 @@
+"""CPU oracle for the decoder hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  The engine (gpustack_b200/) never does: it has no CPU path.
+
+GPUStack itself contains no inference arithmetic; the arithmetic of "the
+reference's vLLM backend" lives in third-party vLLM (pinned vllm==0.10.1.1 in the reference's
+pyproject.toml:97, 0.22.0 installed here).  Each function below restates one operator of that
+engine in plain PyTorch-CPU fp32 with bf16 rounding at the points where the engine stores bf16,
+citing the vLLM file it follows ($VLLM = site-packages/vllm).
+
+Pinning: tests/golden/make_golden.py imports vLLM's own pure-PyTorch implementations
+(vllm.ir.ops.layernorm, RotaryEmbedding.forward_static, SiluAndMul.forward_native) and HF
+transformers' LlamaForCausalLM in the build container and commits their outputs as fixtures;
+tests/test_oracle_golden.py checks this oracle against them.  The reference publishes no golden
+vectors for inference, so those generated fixtures are the pin.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+BF16 = torch.bfloat16
+
+
+def _bf(x: torch.Tensor) -> torch.Tensor:
+    """round to bf16 and come back to fp32 (models a bf16 store)."""
+    return x.to(BF16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------- operators
+def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    """$VLLM/ir/ops/layernorm.py:10-21 -- fp32 stats, cast to weight dtype, multiply."""
+    xf = x.to(torch.float32)
+    var = xf.pow(2).mean(dim=-1, keepdim=True)
+    xn = xf * torch.rsqrt(var + eps)
+    return (xn.to(w.dtype) * w).to(x.dtype)
+
+
+def fused_add_rms_norm(x, residual, w, eps):
+    """$VLLM/ir/ops/layernorm.py:40-58 -- returns (normed, new_residual)."""
+    z = x.to(torch.float32) + residual.to(torch.float32)
+    new_res = z.to(x.dtype)
+    var = z.pow(2).mean(dim=-1, keepdim=True)
+    zn = z * torch.rsqrt(var + eps)
+    return (zn.to(w.dtype) * w).to(x.dtype), new_res
+
+
+def cos_sin_cache(head_dim: int, max_pos: int, base: float, dtype=BF16) -> torch.Tensor:
+    """$VLLM/model_executor/layers/rotary_embedding/base.py:71-93 -- [max_pos, head_dim] = cos|sin."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float) / head_dim))
+    t = torch.arange(max_pos, dtype=torch.float)
+    freqs = torch.einsum("i,j -> ij", t, inv_freq)
+    return torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(dtype)
+
+
+def rope_neox(x: torch.Tensor, positions: torch.Tensor, cache: torch.Tensor) -> torch.Tensor:
+    """$VLLM/model_executor/layers/rotary_embedding/base.py:150-180 + common.py:144-183.
+    x [T, heads, D]; cos/sin come from the cache in the model dtype; the rotation itself is done
+    here in fp32 and rounded once (the engine's kernel does the same; vLLM's native path rounds
+    every bf16 op, which differs by < 2 bf16 ulp -- covered by the stated tolerance)."""
+    D = x.shape[-1]
+    cs = cache.index_select(0, positions.long()).to(torch.float32)
+    cos, sin = cs[:, : D // 2].unsqueeze(1), cs[:, D // 2 :].unsqueeze(1)
+    xf = x.to(torch.float32)
+    x1, x2 = xf[..., : D // 2], xf[..., D // 2 :]
+    return torch.cat((x1 * cos - x2 * sin, x2 * cos + x1 * sin), dim=-1).to(x.dtype)
+
+
+def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    """$VLLM/model_executor/layers/activation.py:133-143 (forward_native): silu in the model dtype,
+    then the product."""
+    d = x.shape[-1] // 2
+    return torch.nn.functional.silu(x[..., :d]) * x[..., d:]
+
+
+def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """$VLLM/model_executor/layers/utils.py:92-98 -- F.linear, fp32 accumulation, bf16 result."""
+    return (x.to(torch.float32) @ w.to(torch.float32).t()).to(x.dtype)
+
+
+def attention_ref(q, k, v, scale: float, q_pos: torch.Tensor) -> torch.Tensor:
+    """Causal GQA attention over a contiguous K/V history.
+    q [Tq, Hq, D], k/v [Tk, Hkv, D]; query i may see keys 0..q_pos[i].  fp32 softmax.
+    ($VLLM/model_executor/models/llama.py:161 scale = head_dim**-0.5; flashinfer.py:1095-1230.)"""
+    Tq, Hq, D = q.shape
+    Tk, Hkv, _ = k.shape
+    G = Hq // Hkv
+    qf = q.to(torch.float32).view(Tq, Hkv, G, D)
+    kf, vf = k.to(torch.float32), v.to(torch.float32)
+    s = torch.einsum("thgd,khd->thgk", qf, kf) * scale
+    mask = torch.arange(Tk).view(1, 1, 1, Tk) > q_pos.view(Tq, 1, 1, 1)
+    s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("thgk,khd->thgd", p, vf)
+    return o.reshape(Tq, Hq, D).to(q.dtype)
+
+
+def gather_paged(cache: torch.Tensor, block_table_row: Sequence[int], n_tokens: int) -> torch.Tensor:
+    """cache [num_blocks, Hkv, block, D] -> contiguous [n_tokens, Hkv, D] for one sequence."""
+    bs = cache.shape[2]
+    pages = [cache[int(b)] for b in block_table_row[: (n_tokens + bs - 1) // bs]]
+    kv = torch.cat(pages, dim=1).transpose(0, 1)  # [tokens, Hkv, D]
+    return kv[:n_tokens]
+
+
+# ----------------------------------------------------------------------------------- model
+@dataclass
+class LlamaConfig:
+    vocab_size: int
+    hidden_size: int
+    intermediate_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    head_dim: int
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    max_position_embeddings: int = 8192
+    tie_word_embeddings: bool = False
+
+    @property
+    def q_size(self):
+        return self.num_attention_heads * self.head_dim
+
+    @property
+    def kv_size(self):
+        return self.num_key_value_heads * self.head_dim
+
+
+TINY = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                   num_attention_heads=8, num_key_value_heads=2, head_dim=64, max_position_embeddings=512)
+TINY128 = LlamaConfig(vocab_size=640, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=1, head_dim=128,
+                      max_position_embeddings=1024)
+QWEN2_05B_SHAPE = LlamaConfig(vocab_size=151936, hidden_size=896, intermediate_size=4864,
+                              num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2,
+                              head_dim=64, rms_norm_eps=1e-6, rope_theta=1e6,
+                              max_position_embeddings=32768, tie_word_embeddings=True)
+LLAMA3_8B = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                        num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, head_dim=128)
+
+
+def init_weights(cfg: LlamaConfig, seed: int = 0, std: float = 0.02, device="cpu") -> Dict[str, torch.Tensor]:
+    """Seeded N(0, std) bf16 weights in HF naming, norm weights 1 + N(0, 0.1) so the norm multiply
+    is exercised.  Generated layer by layer on `device` (use the GPU for the 8B shape)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def rnd(*shape, s=std):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * s).to(BF16)
+
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    w = {"model.embed_tokens.weight": rnd(cfg.vocab_size, H)}
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        w[p + "input_layernorm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
+        w[p + "self_attn.q_proj.weight"] = rnd(cfg.q_size, H)
+        w[p + "self_attn.k_proj.weight"] = rnd(cfg.kv_size, H)
+        w[p + "self_attn.v_proj.weight"] = rnd(cfg.kv_size, H)
+        w[p + "self_attn.o_proj.weight"] = rnd(H, cfg.q_size)
+        w[p + "post_attention_layernorm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
+        w[p + "mlp.gate_proj.weight"] = rnd(I, H)
+        w[p + "mlp.up_proj.weight"] = rnd(I, H)
+        w[p + "mlp.down_proj.weight"] = rnd(H, I)
+    w["model.norm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
+    if not cfg.tie_word_embeddings:
+        w["lm_head.weight"] = rnd(cfg.vocab_size, H)
+    return w
+
+
+class OracleLlama:
+    """Restates LlamaModel.forward / LlamaDecoderLayer.forward
+    ($VLLM/model_executor/models/llama.py:316-333, 395-434) with a plain contiguous KV history per
+    sequence.  bf16 tensors between operators, fp32 inside them."""
+
+    def __init__(self, cfg: LlamaConfig, weights: Dict[str, torch.Tensor]):
+        self.cfg = cfg
+        self.w = {k: v.to("cpu") for k, v in weights.items()}
+        self.cache = cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta)
+        self.lm_head = self.w.get("lm_head.weight", self.w["model.embed_tokens.weight"])
+        self.kv: Dict[int, List] = {}
+
+    def reset(self):
+        self.kv = {}
+
+    def forward(self, seq_id: int, tokens: Sequence[int]) -> torch.Tensor:
+        """Append `tokens` to sequence `seq_id`; returns fp32 logits [len(tokens), vocab]."""
+        cfg, w = self.cfg, self.w
+        hist = self.kv.setdefault(seq_id, [None] * cfg.num_hidden_layers)
+        start = 0 if hist[0] is None else hist[0][0].shape[0]
+        T = len(tokens)
+        pos = torch.arange(start, start + T)
+        h = w["model.embed_tokens.weight"][torch.tensor(list(tokens))]
+        res = None
+        scale = cfg.head_dim ** -0.5
+        for l in range(cfg.num_hidden_layers):
+            p = f"model.layers.{l}."
+            if res is None:
+                res, x = h, rms_norm(h, w[p + "input_layernorm.weight"], cfg.rms_norm_eps)
+            else:
+                x, res = fused_add_rms_norm(h, res, w[p + "input_layernorm.weight"], cfg.rms_norm_eps)
+            q = linear(x, w[p + "self_attn.q_proj.weight"]).view(T, cfg.num_attention_heads, cfg.head_dim)
+            k = linear(x, w[p + "self_attn.k_proj.weight"]).view(T, cfg.num_key_value_heads, cfg.head_dim)
+            v = linear(x, w[p + "self_attn.v_proj.weight"]).view(T, cfg.num_key_value_heads, cfg.head_dim)
+            q, k = rope_neox(q, pos, self.cache), rope_neox(k, pos, self.cache)
+            if hist[l] is None:
+                hist[l] = (k, v)
+            else:
+                hist[l] = (torch.cat((hist[l][0], k)), torch.cat((hist[l][1], v)))
+            a = attention_ref(q, hist[l][0], hist[l][1], scale, pos).reshape(T, cfg.q_size)
+            h = linear(a, w[p + "self_attn.o_proj.weight"])
+            x, res = fused_add_rms_norm(h, res, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
+            gu = torch.cat((linear(x, w[p + "mlp.gate_proj.weight"]), linear(x, w[p + "mlp.up_proj.weight"])), dim=-1)
+            h = linear(silu_and_mul(gu), w[p + "mlp.down_proj.weight"])
+        x, _ = fused_add_rms_norm(h, res, w["model.norm.weight"], cfg.rms_norm_eps)
+        return x.to(torch.float32) @ self.lm_head.to(torch.float32).t()
+
+    def generate(self, seq_id: int, prompt: Sequence[int], max_new_tokens: int) -> List[int]:
+        """greedy decode ($VLLM/v1/sample/sampler.py: argmax over fp32 logits, lowest index wins)."""
+        out: List[int] = []
+        logits = self.forward(seq_id, prompt)[-1]
+        for _ in range(max_new_tokens):
+            nxt = int(torch.argmax(logits))
+            out.append(nxt)
+            if len(out) == max_new_tokens:
+                break
+            logits = self.forward(seq_id, [nxt])[-1]
+        return out
+
+
+def to_hf_state_dict(weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    return dict(weights)

@@ -1,0 +1,90 @@
+"""Generate the golden fixtures that pin oracle/llama_oracle.py.
+
+Run in the BUILD container (no GPU needed):  python tests/golden/make_golden.py
+Sources of truth imported here (never at test time on the GPU box):
+  * vLLM 0.22.0's own pure-PyTorch operator definitions -- the engine GPUStack's vLLM backend
+    launches (gpustack/worker/backends/vllm.py:403-407): vllm.ir.ops.layernorm.{rms_norm,
+    fused_add_rms_norm}, RotaryEmbedding.forward_static (neox), SiluAndMul.forward_native;
+  * HF transformers LlamaForCausalLM (eager attention) for whole-model logits and greedy tokens
+    of the seeded tiny Llama configs.
+Outputs: tests/golden/ops_vllm.pt, tests/golden/tiny_llama_hf.pt (a few hundred KB).
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import llama_oracle as O  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+BF = torch.bfloat16
+
+
+def ops_from_vllm():
+    from vllm.ir.ops.layernorm import fused_add_rms_norm, rms_norm
+    from vllm.model_executor.layers.activation import SiluAndMul
+    from vllm.model_executor.layers.rotary_embedding.base import RotaryEmbedding
+
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    x = (torch.randn(6, 512, generator=g) * 1.5).to(BF)
+    r = torch.randn(6, 512, generator=g).to(BF)
+    w = (1 + 0.1 * torch.randn(512, generator=g)).to(BF)
+    out["norm_x"], out["norm_res"], out["norm_w"] = x, r, w
+    out["rms_norm"] = rms_norm(x, w, 1e-5)
+    y, nr = fused_add_rms_norm(x.clone(), r.clone(), w, 1e-5)
+    out["fused_y"], out["fused_res"] = y, nr
+
+    for D, theta in ((128, 500000.0), (64, 1e6)):
+        T, Hq, Hkv, max_pos = 9, 4, 2, 256
+        q = torch.randn(T, Hq * D, generator=g).to(BF)
+        k = torch.randn(T, Hkv * D, generator=g).to(BF)
+        pos = torch.randint(0, max_pos, (T,), generator=g)
+        inv_freq = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float) / D))
+        freqs = torch.einsum("i,j -> ij", torch.arange(max_pos, dtype=torch.float), inv_freq)
+        cache = torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(BF)  # base.py:82-93 then .to(dtype)
+        rq, rk = RotaryEmbedding.forward_static(pos, q.clone(), k.clone(), D, D, cache, True)
+        out[f"rope{D}"] = {"q": q, "k": k, "pos": pos, "theta": theta, "max_pos": max_pos,
+                           "cache": cache, "rq": rq, "rk": rk}
+
+    xs = (torch.randn(5, 2 * 384, generator=g) * 2).to(BF)
+    out["silu_x"] = xs
+    out["silu_y"] = SiluAndMul.forward_native(xs)
+    torch.save(out, OUT / "ops_vllm.pt")
+    print("wrote ops_vllm.pt")
+
+
+def tiny_llama_from_hf():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    out = {}
+    for name, cfg in (("tiny", O.TINY), ("tiny128", O.TINY128)):
+        weights = O.init_weights(cfg, seed=7)
+        hf_cfg = LlamaConfig(
+            vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+            num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+            num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim, rms_norm_eps=cfg.rms_norm_eps,
+            rope_theta=cfg.rope_theta, max_position_embeddings=cfg.max_position_embeddings,
+            tie_word_embeddings=False, attention_bias=False, mlp_bias=False, hidden_act="silu",
+            attn_implementation="eager")
+        g = torch.Generator().manual_seed(42)
+        prompt = torch.randint(3, cfg.vocab_size, (1, 23), generator=g)
+        res = {"prompt": prompt[0].tolist()}
+        for dt, key in ((torch.float32, "fp32"), (BF, "bf16")):
+            model = LlamaForCausalLM(hf_cfg).to(dt).eval()
+            missing = model.load_state_dict({k: v.to(dt) for k, v in weights.items()}, strict=True)
+            with torch.no_grad():
+                logits = model(prompt).logits[0].float()
+                gen = model.generate(prompt, max_new_tokens=12, do_sample=False, pad_token_id=0)
+            res[f"logits_{key}"] = logits[-4:].clone()      # last 4 positions are enough to pin
+            res[f"greedy_{key}"] = gen[0, prompt.shape[1]:].tolist()
+        out[name] = res
+    torch.save(out, OUT / "tiny_llama_hf.pt")
+    print("wrote tiny_llama_hf.pt")
+
+
+if __name__ == "__main__":
+    ops_from_vllm()
+    tiny_llama_from_hf()

@@ -1,0 +1,277 @@
+"""Parity of every libb200.so kernel against the CPU oracle (oracle/llama_oracle.py), through the
+C ABI, on seeded inputs.  Tolerances: bf16 results atol 1e-3*scale / rtol 1.6e-2 (vLLM's own bf16
+tolerance, $VLLM/ir/tolerances.py:12-38); integer results (argmax, gathers, cache scatter) exact.
+"""
+import json
+import math
+
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gpustack_b200 import ops as _ops
+
+    _ops.device_info()
+    return _ops
+
+
+def _close(got, ref, atol, rtol, what, out_dir=None):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        info = {
+            "what": what, "max_err": float(err.max()), "ref_absmax": float(ref.abs().max()),
+            "bad_frac": float(bad.float().mean()), "first_bad": idx,
+            "got": [float(got[tuple(i)]) for i in idx], "ref": [float(ref[tuple(i)]) for i in idx],
+        }
+        if got.dim() == 2:
+            info["bad_rows"] = bad.any(dim=1).nonzero().flatten()[:16].tolist()
+            info["bad_cols"] = bad.any(dim=0).nonzero().flatten()[:16].tolist()
+            info["n_bad_rows"] = int(bad.any(dim=1).sum()); info["n_bad_cols"] = int(bad.any(dim=0).sum())
+        if out_dir is not None:
+            with open(out_dir / "parity_failures.jsonl", "a") as f:
+                f.write(json.dumps(info) + "\n")
+        pytest.fail(json.dumps(info))
+
+
+# --------------------------------------------------------------------------------- rmsnorm
+@pytest.mark.parametrize("T,H", [(1, 4096), (7, 4096), (300, 4096), (5, 896), (3, 512), (2, 8192)])
+def test_rms_norm(ops, T, H, out_dir):
+    g = torch.Generator().manual_seed(T * 1000 + H)
+    x = (torch.randn(T, H, generator=g) * 2).to(BF)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(BF)
+    ref = O.rms_norm(x, w, 1e-5)
+    got = ops.rms_norm(x.cuda(), w.cuda(), 1e-5)
+    _close(got, ref, 1e-2, 1.6e-2, f"rms_norm {T}x{H}", out_dir)
+
+
+@pytest.mark.parametrize("T,H", [(1, 4096), (33, 4096), (257, 4096), (4, 896)])
+def test_fused_add_rms_norm(ops, T, H, out_dir):
+    g = torch.Generator().manual_seed(T + H)
+    x = torch.randn(T, H, generator=g).to(BF)
+    r = torch.randn(T, H, generator=g).to(BF)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(BF)
+    ref_y, ref_r = O.fused_add_rms_norm(x, r, w, 1e-5)
+    xc, rc = x.cuda(), r.cuda()
+    y, rr = ops.fused_add_rms_norm(xc, rc, w.cuda(), 1e-5, out=xc, residual_out=rc)  # in place
+    _close(rr, ref_r, 0, 0, "fused_add residual (exact)", out_dir)
+    _close(y, ref_y, 1e-2, 1.6e-2, "fused_add_rms_norm", out_dir)
+
+
+def test_fused_add_rms_norm_partials(ops, out_dir):
+    g = torch.Generator().manual_seed(5)
+    S, T, H = 4, 19, 4096
+    parts = torch.randn(S, T, H, generator=g)
+    r = torch.randn(T, H, generator=g).to(BF)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(BF)
+    z = parts.sum(0) + r.float()
+    ref_r = z.to(BF)
+    ref_y = ((z * torch.rsqrt(z.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF) * w)
+    y = torch.empty(T, H, dtype=BF, device="cuda"); ro = torch.empty_like(y)
+    ops.fused_add_rms_norm_partials(parts.cuda(), r.cuda(), w.cuda(), 1e-5, y, ro)
+    _close(ro, ref_r, 1e-2, 8e-3, "partials residual", out_dir)
+    _close(y, ref_y, 2e-2, 1.6e-2, "partials norm", out_dir)
+
+
+# ------------------------------------------------------------------------ rope + kv write
+@pytest.mark.parametrize("Hq,Hkv,D", [(32, 8, 128), (14, 2, 64), (4, 1, 128)])
+def test_rope_kv_write(ops, Hq, Hkv, D, out_dir):
+    g = torch.Generator().manual_seed(Hq)
+    T, nblk, bs = 37, 12, 16
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * D, generator=g).to(BF)
+    pos = torch.randint(0, 500, (T,), generator=g, dtype=torch.int32)
+    cache = O.cos_sin_cache(D, 512, 500000.0)
+    slots = torch.randperm(nblk * bs, generator=g)[:T].to(torch.int32)
+    slots[3] = -1
+    kc = torch.zeros(nblk, Hkv, bs, D, dtype=BF, device="cuda"); vc = torch.zeros_like(kc)
+    q = qkv[:, : Hq * D].view(T, Hq, D)
+    k = qkv[:, Hq * D : (Hq + Hkv) * D].view(T, Hkv, D)
+    v = qkv[:, (Hq + Hkv) * D :].view(T, Hkv, D)
+    rq, rk = O.rope_neox(q, pos, cache), O.rope_neox(k, pos, cache)
+    dq = qkv.cuda()
+    ops.rope_kv_write(dq, pos.cuda(), cache.cuda(), kc, vc, slots.cuda(), Hq, Hkv, D)
+    got = dq.cpu()
+    _close(got[:, : Hq * D].view(T, Hq, D), rq, 1e-2, 8e-3, "rope q", out_dir)
+    _close(got[:, Hq * D : (Hq + Hkv) * D].view(T, Hkv, D), rk, 1e-2, 8e-3, "rope k", out_dir)
+    assert torch.equal(got[:, (Hq + Hkv) * D :], qkv[:, (Hq + Hkv) * D :])
+    kcc, vcc = kc.cpu(), vc.cpu()
+    gk = got[:, Hq * D : (Hq + Hkv) * D].view(T, Hkv, D)
+    for t in range(T):
+        s = int(slots[t])
+        if s < 0:
+            continue
+        assert torch.equal(kcc[s // bs, :, s % bs], gk[t]), f"k cache slot {s}"
+        assert torch.equal(vcc[s // bs, :, s % bs], v[t]), f"v cache slot {s}"
+    used = set(int(s) for s in slots if s >= 0)
+    for s in range(nblk * bs):
+        if s not in used:
+            assert float(kcc[s // bs, :, s % bs].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("T,I", [(1, 14336), (65, 14336), (9, 4864), (300, 1024)])
+def test_silu_and_mul(ops, T, I, out_dir):
+    g = torch.Generator().manual_seed(I)
+    x = (torch.randn(T, 2 * I, generator=g) * 2).to(BF)
+    ref = O.silu_and_mul(x)
+    _close(ops.silu_and_mul(x.cuda()), ref, 1e-2, 1.6e-2, "silu_and_mul", out_dir)
+
+
+def test_embedding_gather_argmax(ops):
+    g = torch.Generator().manual_seed(1)
+    V, H, T = 1000, 512, 77
+    table = torch.randn(V, H, generator=g).to(BF)
+    ids = torch.randint(0, V, (T,), generator=g, dtype=torch.int32)
+    got = ops.embedding(ids.cuda(), table.cuda()).cpu()
+    assert torch.equal(got, table[ids.long()])
+    # vocab-parallel shard: rows outside [300, 600) come back as zeros
+    shard = ops.embedding(ids.cuda(), table[300:600].contiguous().cuda(), vocab_start=300, vocab_end=600).cpu()
+    ref = table[ids.long()].clone(); ref[(ids < 300) | (ids >= 600)] = 0
+    assert torch.equal(shard, ref)
+    rows = torch.randint(0, T, (13,), generator=g, dtype=torch.int32)
+    assert torch.equal(ops.gather_rows(got.cuda(), rows.cuda()).cpu(), got[rows.long()])
+    for B, Vv in [(1, 128256), (5, 128256), (3, 1001), (2, 7)]:
+        lg = torch.randn(B, Vv, generator=g)
+        lg[0, Vv // 2] = 50.0; lg[0, Vv - 1] = 50.0  # tie: lowest index must win
+        idx = ops.argmax(lg.cuda()).cpu()
+        assert idx.tolist() == [int(torch.argmax(r)) if i else Vv // 2 for i, r in enumerate(lg)]
+
+
+# ------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # M, N, K, splits, f32
+    (1, 256, 128, 1, 0), (16, 128, 64, 1, 0), (5, 384, 512, 1, 0),
+    (1, 4096, 4096, 1, 0), (16, 6144, 4096, 1, 0), (33, 4096, 4096, 1, 0), (64, 4096, 14336, 1, 0),
+    (100, 28672, 4096, 1, 0), (128, 4096, 4096, 1, 0), (256, 6144, 4096, 1, 0),
+    (200, 1000, 896, 1, 0),        # N tail (not a multiple of 128), M tail
+    (64, 16032, 4096, 1, 0),       # vocab shard of TP=8
+    (512, 6144, 4096, 1, 0), (1000, 4096, 4096, 1, 0), (2048, 4096, 14336, 1, 0),
+    (8, 128256, 4096, 1, 1),       # lm_head, fp32 logits
+    (64, 4096, 14336, 4, 1), (7, 4096, 4096, 8, 1), (256, 4096, 4096, 2, 1),  # split-K partials
+]
+
+
+@pytest.mark.parametrize("M,N,K,splits,f32", GEMM_SHAPES)
+def test_gemm(ops, M, N, K, splits, f32, out_dir):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(BF)
+    ref = x.double() @ w.double().t()
+    scale = 0.02 * math.sqrt(K)
+    if splits > 1:
+        parts = ops.gemm(x, w, splits=splits)
+        assert parts.shape == (splits, M, N) and parts.dtype == torch.float32
+        _close(parts.double().sum(0), ref, 2e-3 * scale, 2e-3, f"gemm splitK {M}x{N}x{K}/{splits}", out_dir)
+        y = ops.splitk_reduce(parts)
+        _close(y, ref, 1e-2 * scale, 1.6e-2, "splitk_reduce", out_dir)
+    elif f32:
+        y = ops.gemm(x, w, out_dtype=torch.float32)
+        _close(y, ref, 2e-3 * scale, 2e-3, f"gemm f32 {M}x{N}x{K}", out_dir)
+    else:
+        y = ops.gemm(x, w)
+        _close(y, ref, 1e-2 * scale, 1.6e-2, f"gemm {M}x{N}x{K}", out_dir)
+
+
+def test_gemm_vs_cpu_oracle(ops, out_dir):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(40, 512, generator=g).to(BF); w = (torch.randn(640, 512, generator=g) * 0.05).to(BF)
+    _close(ops.gemm(x.cuda(), w.cuda()), O.linear(x, w), 1e-2, 1.6e-2, "gemm vs oracle.linear", out_dir)
+
+
+def test_gemm_strided_views(ops, out_dir):
+    """column-sliced activations (q part of qkv) and row-sliced weights are passed as views."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    big = torch.randn(50, 1024, generator=g, device="cuda").to(BF)
+    w = (torch.randn(300, 2048, generator=g, device="cuda") * 0.03).to(BF)
+    x = big[:, 256:768]            # ld 1024, K 512
+    wv = w[:, 512:1024]            # ld 2048
+    ref = x.double() @ wv.double().t()
+    _close(ops.gemm(x, wv), ref, 1e-2, 1.6e-2, "gemm strided", out_dir)
+
+
+# ------------------------------------------------------------------------------- attention
+def _make_paged(g, seq_lens, Hkv, D, extra_blocks=5):
+    bs = 16
+    n_pages = [(n + bs - 1) // bs for n in seq_lens]
+    total = sum(n_pages) + extra_blocks
+    perm = torch.randperm(total, generator=g)
+    max_blocks = max(n_pages) + 2
+    bt = torch.zeros(len(seq_lens), max_blocks, dtype=torch.int32)
+    kc = torch.randn(total, Hkv, bs, D, generator=g).to(BF)
+    vc = torch.randn(total, Hkv, bs, D, generator=g).to(BF)
+    off = 0
+    for i, n in enumerate(n_pages):
+        bt[i, :n] = perm[off : off + n].to(torch.int32)
+        off += n
+    return kc, vc, bt
+
+
+@pytest.mark.parametrize("Hq,Hkv,D,seq_lens,splits", [
+    (32, 8, 128, [1, 17, 576, 33, 640, 100], 1),
+    (32, 8, 128, [2000, 5, 1023], 4),
+    (14, 2, 64, [77, 300, 16, 15], 1),
+    (14, 2, 64, [900, 31], 3),
+    (4, 1, 128, [8192], 16),
+    (8, 8, 128, [50, 130], 1),
+])
+def test_paged_attn_decode(ops, Hq, Hkv, D, seq_lens, splits, out_dir):
+    g = torch.Generator().manual_seed(sum(seq_lens))
+    B = len(seq_lens)
+    kc, vc, bt = _make_paged(g, seq_lens, Hkv, D)
+    stride = (Hq + 2 * Hkv) * D
+    qkv = torch.randn(B, stride, generator=g).to(BF)
+    scale = D ** -0.5
+    ref = torch.empty(B, Hq * D, dtype=BF)
+    for b, n in enumerate(seq_lens):
+        k = O.gather_paged(kc, bt[b].tolist(), n); v = O.gather_paged(vc, bt[b].tolist(), n)
+        q = qkv[b, : Hq * D].view(1, Hq, D)
+        ref[b] = O.attention_ref(q, k, v, scale, torch.tensor([n - 1])).reshape(-1)
+    dq = qkv.cuda()
+    out = torch.empty(B, Hq * D, dtype=BF, device="cuda")
+    ws = ops.attn_decode_workspace(B, Hq, D, splits, "cuda")
+    ops.paged_attn_decode(dq, stride, kc.cuda(), vc.cuda(), bt.cuda(), torch.tensor(seq_lens, dtype=torch.int32).cuda(),
+                          out, Hq, Hkv, D, scale, num_splits=splits, workspace=ws)
+    _close(out, ref, 2e-2, 1.6e-2, f"attn_decode Hq{Hq} D{D} splits{splits}", out_dir)
+
+
+@pytest.mark.parametrize("Hq,Hkv,D,ctx_q", [
+    (32, 8, 128, [(0, 512), (0, 1), (0, 33), (0, 100)]),
+    (32, 8, 128, [(512, 64), (100, 17), (31, 300)]),     # chunked prefill / prefix continuation
+    (14, 2, 64, [(0, 130), (20, 50)]),
+    (4, 1, 128, [(0, 1500)]),
+    (16, 2, 128, [(0, 70), (5, 9)]),                      # group of 8 -> 16-token tiles
+])
+def test_paged_attn_prefill(ops, Hq, Hkv, D, ctx_q, out_dir):
+    g = torch.Generator().manual_seed(len(ctx_q) * 31 + Hq)
+    totals = [c + n for c, n in ctx_q]
+    kc, vc, bt = _make_paged(g, totals, Hkv, D)
+    q_lens = [n for _, n in ctx_q]
+    T = sum(q_lens)
+    stride = (Hq + 2 * Hkv) * D
+    qkv = torch.randn(T, stride, generator=g).to(BF)
+    scale = D ** -0.5
+    cu = [0]
+    for n in q_lens:
+        cu.append(cu[-1] + n)
+    ref = torch.empty(T, Hq * D, dtype=BF)
+    for s, (c, n) in enumerate(ctx_q):
+        k = O.gather_paged(kc, bt[s].tolist(), c + n); v = O.gather_paged(vc, bt[s].tolist(), c + n)
+        q = qkv[cu[s] : cu[s + 1], : Hq * D].reshape(n, Hq, D)
+        ref[cu[s] : cu[s + 1]] = O.attention_ref(q, k, v, scale, torch.arange(c, c + n)).reshape(n, -1)
+    tile = ops.attn_prefill_tile(Hq, Hkv)
+    ts, tq = ops.build_prefill_tiles(q_lens, tile)
+    i32 = lambda a: torch.tensor(a, dtype=torch.int32, device="cuda")
+    out = torch.zeros(T, Hq * D, dtype=BF, device="cuda")
+    ops.paged_attn_prefill(qkv.cuda(), stride, kc.cuda(), vc.cuda(), bt.cuda(), i32(cu), i32([c for c, _ in ctx_q]),
+                           i32(ts), i32(tq), out, Hq, Hkv, D, scale)
+    _close(out, ref, 2e-2, 1.6e-2, f"attn_prefill Hq{Hq} D{D}", out_dir)
