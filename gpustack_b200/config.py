@@ -1,0 +1,143 @@
+"""Model and engine configuration.
+
+ModelConfig is read from the HF-format `config.json` inside the local model directory that
+GPUStack mounts and passes as {{model_path}} (gpustack/worker/backends/custom.py:91-134).
+EngineConfig mirrors the subset of vLLM's CLI that GPUStack's launcher composes
+(gpustack/worker/backends/vllm.py:395-507): --max-model-len, --tensor-parallel-size,
+--gpu-memory-utilization, --max-num-seqs, --max-num-batched-tokens, --served-model-name.
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Optional
+
+SUPPORTED_ARCHS = ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM")
+
+
+@dataclass
+class ModelConfig:
+    vocab_size: int
+    hidden_size: int
+    intermediate_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    head_dim: int
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    max_position_embeddings: int = 8192
+    tie_word_embeddings: bool = False
+    attention_bias: bool = False
+    architecture: str = "LlamaForCausalLM"
+    eos_token_id: Optional[int] = None
+    bos_token_id: Optional[int] = None
+
+    @property
+    def q_size(self) -> int:
+        return self.num_attention_heads * self.head_dim
+
+    @property
+    def kv_size(self) -> int:
+        return self.num_key_value_heads * self.head_dim
+
+    def kv_bytes_per_token(self, tp: int = 1) -> int:
+        return 2 * self.num_hidden_layers * (self.num_key_value_heads // tp) * self.head_dim * 2
+
+    def weight_bytes(self, tp: int = 1) -> int:
+        """bf16 bytes streamed per decode step on one rank (layers + lm_head + final norm)."""
+        H, I = self.hidden_size, self.intermediate_size
+        per_layer = (self.q_size + 2 * self.kv_size) * H + self.q_size * H + 3 * I * H
+        return 2 * (self.num_hidden_layers * per_layer // tp + self.vocab_size * H // tp + H)
+
+    @staticmethod
+    def from_dict(d: dict) -> "ModelConfig":
+        archs = d.get("architectures") or ["LlamaForCausalLM"]
+        arch = archs[0]
+        if arch not in SUPPORTED_ARCHS:
+            raise ValueError(f"unsupported architecture {arch}; supported: {SUPPORTED_ARCHS}")
+        heads = d["num_attention_heads"]
+        eos = d.get("eos_token_id")
+        if isinstance(eos, list):
+            eos = eos[0] if eos else None
+        rope = d.get("rope_theta")
+        if rope is None and isinstance(d.get("rope_parameters"), dict):
+            rope = d["rope_parameters"].get("rope_theta")
+        scaling = d.get("rope_scaling") or (d.get("rope_parameters") or {}).get("rope_type")
+        if isinstance(scaling, dict) and scaling.get("rope_type", scaling.get("type")) not in (None, "default"):
+            raise ValueError("rope_scaling other than default is not supported yet")
+        return ModelConfig(
+            vocab_size=d["vocab_size"], hidden_size=d["hidden_size"],
+            intermediate_size=d["intermediate_size"], num_hidden_layers=d["num_hidden_layers"],
+            num_attention_heads=heads, num_key_value_heads=d.get("num_key_value_heads", heads),
+            head_dim=d.get("head_dim") or d["hidden_size"] // heads,
+            rms_norm_eps=d.get("rms_norm_eps", 1e-5), rope_theta=float(rope or 10000.0),
+            max_position_embeddings=d.get("max_position_embeddings", 8192),
+            tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
+            attention_bias=bool(d.get("attention_bias", arch == "Qwen2ForCausalLM")),
+            architecture=arch, eos_token_id=eos, bos_token_id=d.get("bos_token_id"))
+
+    @staticmethod
+    def from_pretrained(model_path: str) -> "ModelConfig":
+        with open(Path(model_path) / "config.json") as f:
+            return ModelConfig.from_dict(json.load(f))
+
+    def to_hf_dict(self) -> dict:
+        return {
+            "architectures": [self.architecture], "model_type": "llama", "vocab_size": self.vocab_size,
+            "hidden_size": self.hidden_size, "intermediate_size": self.intermediate_size,
+            "num_hidden_layers": self.num_hidden_layers, "num_attention_heads": self.num_attention_heads,
+            "num_key_value_heads": self.num_key_value_heads, "head_dim": self.head_dim,
+            "rms_norm_eps": self.rms_norm_eps, "rope_theta": self.rope_theta,
+            "max_position_embeddings": self.max_position_embeddings,
+            "tie_word_embeddings": self.tie_word_embeddings, "attention_bias": self.attention_bias,
+            "hidden_act": "silu", "torch_dtype": "bfloat16", "bos_token_id": self.bos_token_id or 1,
+            "eos_token_id": self.eos_token_id if self.eos_token_id is not None else 2,
+        }
+
+
+# Named shapes used by tests and bench (random-init; there are no checkpoints offline).
+def llama3_8b() -> ModelConfig:
+    return ModelConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                       num_attention_heads=32, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
+                       rope_theta=500000.0, max_position_embeddings=8192, eos_token_id=128001,
+                       bos_token_id=128000)
+
+
+def tiny_llama(head_dim: int = 64) -> ModelConfig:
+    if head_dim == 128:
+        return ModelConfig(vocab_size=640, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                           num_attention_heads=4, num_key_value_heads=1, head_dim=128,
+                           max_position_embeddings=1024, eos_token_id=2, bos_token_id=1)
+    return ModelConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                       num_attention_heads=8, num_key_value_heads=2, head_dim=64,
+                       max_position_embeddings=512, eos_token_id=2, bos_token_id=1)
+
+
+@dataclass
+class EngineConfig:
+    model: str = ""
+    served_model_name: Optional[str] = None
+    max_model_len: Optional[int] = None
+    tensor_parallel_size: int = 1
+    gpu_memory_utilization: float = 0.90
+    max_num_seqs: int = 256
+    max_num_batched_tokens: int = 8192
+    num_gpu_blocks: Optional[int] = None      # override the memory-derived KV block count
+    enforce_eager: bool = False               # skip CUDA-graph capture of decode steps
+    seed: int = 0
+    block_size: int = 16
+    cuda_graph_sizes: list = field(default_factory=list)
+
+    def graph_buckets(self) -> list:
+        if self.cuda_graph_sizes:
+            return sorted(set(min(b, self.max_num_seqs) for b in self.cuda_graph_sizes))
+        b = [1, 2, 4, 8]
+        b += list(range(16, 129, 8))
+        b += list(range(144, 513, 16))
+        b += list(range(544, 1025, 32))
+        b = [x for x in b if x <= self.max_num_seqs]
+        if self.max_num_seqs not in b:
+            b.append(self.max_num_seqs)
+        return sorted(set(b))

@@ -1,0 +1,219 @@
+"""Engine core: scheduler + model runner + (optional) tensor-parallel step broadcast.
+
+Counterpart of the reference engine's EngineCore busy loop ($VLLM/v1/engine/core.py): one
+iteration = schedule -> execute on the GPU -> update request state -> emit new tokens.
+With tensor parallelism there is one process per GPU (torch.distributed, NCCL for tensors);
+rank 0 owns the scheduler and broadcasts each step's inputs, the other ranks replay the same
+kernel sequence on their weight / KV shards (TPWorker.serve_forever).
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .config import EngineConfig, ModelConfig
+from .lib import B200Error
+from .runner import ModelRunner
+from .scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
+from .weights import ModelWeights, load_safetensors_dir, random_state_dict, shard_state_dict
+
+_KIND_STOP, _KIND_DECODE, _KIND_PREFILL = 0, 1, 2
+
+
+class TPContext:
+    """torch.distributed plumbing for one tensor-parallel group (one process per GPU)."""
+
+    def __init__(self, rank: int, world: int, device: torch.device):
+        import torch.distributed as dist
+
+        self.rank, self.world, self.device = rank, world, device
+        self.dist = dist
+        self.nccl = dist.group.WORLD
+        self.cpu = dist.new_group(backend="gloo")   # step metadata travels over gloo
+
+    @staticmethod
+    def from_env() -> Optional["TPContext"]:
+        import torch.distributed as dist
+
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1:
+            return None
+        rank = int(os.environ["RANK"])
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        return TPContext(rank, world, torch.device("cuda", local))
+
+    def bcast_step(self, header: List[int], payload: Optional[np.ndarray]):
+        """rank 0 sends (header, int32 payload); the other ranks receive them."""
+        h = torch.zeros(8, dtype=torch.int64)
+        if self.rank == 0:
+            h[:len(header)] = torch.tensor(header, dtype=torch.int64)
+            h[7] = 0 if payload is None else len(payload)
+        self.dist.broadcast(h, src=0, group=self.cpu)
+        n = int(h[7])
+        if n:
+            t = torch.from_numpy(np.ascontiguousarray(payload)) if self.rank == 0 else torch.empty(n, dtype=torch.int32)
+            self.dist.broadcast(t, src=0, group=self.cpu)
+            payload = t.numpy()
+        return h.tolist(), payload
+
+
+class LLMEngine:
+    def __init__(self, mcfg: ModelConfig, ecfg: EngineConfig, weights: ModelWeights, tp: Optional[TPContext] = None,
+                 device: str = "cuda"):
+        self.mcfg, self.ecfg, self.tp = mcfg, ecfg, tp
+        if ecfg.max_model_len is None:
+            ecfg.max_model_len = mcfg.max_position_embeddings
+        ecfg.max_model_len = min(ecfg.max_model_len, mcfg.max_position_embeddings)
+        self.runner = ModelRunner(mcfg, ecfg, weights, device=device, tp_group=tp.nccl if tp else None)
+        n = self.runner.profile_num_blocks()
+        if tp:   # every rank must use the same block count
+            t = torch.tensor([n], dtype=torch.int64)
+            tp.dist.all_reduce(t, op=tp.dist.ReduceOp.MIN, group=tp.cpu)
+            n = int(t[0])
+        self.num_blocks = n
+        self.runner.init_kv_cache(n)
+        self.runner.capture_graphs()
+        self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
+                               ecfg.max_model_len, mcfg.eos_token_id)
+        self.requests: Dict[str, Request] = {}
+        self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
+        self.step_time = {"prefill": 0.0, "decode": 0.0}
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_engine_config(cls, ecfg: EngineConfig, mcfg: Optional[ModelConfig] = None,
+                           state_dict: Optional[dict] = None) -> "LLMEngine":
+        """Model from `ecfg.model` (an HF-format directory), or from an explicit state dict, or --
+        when ecfg.model is 'random:<name>' / mcfg is given without weights -- seeded random init."""
+        tp = TPContext.from_env() if ecfg.tensor_parallel_size > 1 else None
+        if ecfg.tensor_parallel_size > 1 and (tp is None or tp.world != ecfg.tensor_parallel_size):
+            raise B200Error(f"tensor_parallel_size={ecfg.tensor_parallel_size} needs WORLD_SIZE to match "
+                            "(launch one process per GPU, e.g. with torch.distributed.run)")
+        rank = tp.rank if tp else 0
+        device = f"cuda:{torch.cuda.current_device()}"
+        if state_dict is None and mcfg is None:
+            mcfg = ModelConfig.from_pretrained(ecfg.model)
+            weights = load_safetensors_dir(mcfg, ecfg.model, rank, ecfg.tensor_parallel_size, device)
+        else:
+            if state_dict is None:
+                state_dict = random_state_dict(mcfg, seed=ecfg.seed, device=device)
+            weights = shard_state_dict(mcfg, lambda k: state_dict[k], rank, ecfg.tensor_parallel_size, device)
+            del state_dict
+            torch.cuda.empty_cache()
+        return cls(mcfg, ecfg, weights, tp=tp, device=device)
+
+    # ------------------------------------------------------------------ request side
+    def add_request(self, req_id: str, prompt_ids: Sequence[int], params: SamplingParams) -> None:
+        if req_id in self.requests:
+            raise ValueError(f"duplicate request id {req_id}")
+        V = self.mcfg.vocab_size
+        if any((t < 0 or t >= V) for t in prompt_ids):
+            raise ValueError("prompt token id out of range")
+        need = (len(prompt_ids) + params.max_tokens + self.ecfg.block_size) // self.ecfg.block_size
+        if need > self.sched.pool.num_total:
+            raise ValueError("request does not fit in the KV cache")
+        r = Request(req_id=req_id, prompt_ids=list(prompt_ids), params=params)
+        self.sched.add(r)
+        self.requests[req_id] = r
+        self.counters["prompt_tokens"] += len(prompt_ids)
+
+    def abort_request(self, req_id: str) -> None:
+        if self.sched.abort(req_id):
+            self.requests.pop(req_id, None)
+
+    def has_work(self) -> bool:
+        return self.sched.has_work()
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self) -> Optional[StepOutput]:
+        plan = self.sched.schedule()
+        if plan is None:
+            return None
+        t0 = time.perf_counter()
+        if isinstance(plan, DecodePlan):
+            B = plan.batch
+            s = self.sched
+            if self.tp:
+                payload = np.concatenate([s.last_token[:B], s.num_computed[:B], s.block_table[:B].reshape(-1)])
+                self.tp.bcast_step([_KIND_DECODE, B], payload.astype(np.int32))
+            toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table)
+            out = s.update_decode(plan, toks)
+            self.step_time["decode"] += time.perf_counter() - t0
+        else:
+            chunks = [r.all_ids[st:st + n] for r, st, n in zip(plan.reqs, plan.starts, plan.lens)]
+            tables = [r.blocks for r in plan.reqs]
+            if self.tp:
+                self._bcast_prefill(chunks, plan.starts, tables, plan.sample)
+            toks = self.runner.prefill(chunks, plan.starts, tables, plan.sample)
+            out = self.sched.update_prefill(plan, toks)
+            self.step_time["prefill"] += time.perf_counter() - t0
+        self.counters["steps"] += 1
+        self.counters["generation_tokens"] += len(out.token_ids)
+        for rid, fin in zip(out.req_ids, out.finished):
+            if fin is not None:
+                self.counters["finished"] += 1
+                self.requests.pop(rid, None)
+        return out
+
+    def _bcast_prefill(self, chunks, starts, tables, sample) -> None:
+        S = len(chunks)
+        lens = [len(c) for c in chunks]
+        nb = [len(t) for t in tables]
+        flat = np.concatenate([np.asarray(lens), np.asarray(starts), np.asarray(sample, dtype=np.int32),
+                               np.asarray(nb)] + [np.asarray(t) for t in tables] +
+                              [np.asarray(c) for c in chunks]).astype(np.int32)
+        self.tp.bcast_step([_KIND_PREFILL, S], flat)
+
+    def shutdown(self) -> None:
+        if self.tp and self.tp.rank == 0:
+            self.tp.bcast_step([_KIND_STOP], None)
+
+    # ------------------------------------------------------------------ offline API
+    def generate(self, prompts: Sequence[Sequence[int]], params: SamplingParams | Sequence[SamplingParams]) -> List[List[int]]:
+        """Run the given token-id prompts to completion (continuous batching); returns output ids."""
+        reqs = []
+        for i, p in enumerate(prompts):
+            sp = params if isinstance(params, SamplingParams) else params[i]
+            rid = f"gen-{self.counters['finished']}-{i}-{time.monotonic_ns()}"
+            self.add_request(rid, p, sp)
+            reqs.append(self.requests[rid])
+        while self.has_work():
+            self.step()
+        return [r.output_ids for r in reqs]
+
+
+class TPWorker:
+    """Ranks > 0 of a tensor-parallel group: replay rank 0's steps on the local shard."""
+
+    def __init__(self, engine: LLMEngine):
+        self.engine = engine
+
+    def serve_forever(self) -> None:
+        tp, run = self.engine.tp, self.engine.runner
+        mb = run.max_blocks
+        while True:
+            h, p = tp.bcast_step([0], None)
+            kind = h[0]
+            if kind == _KIND_STOP:
+                return
+            if kind == _KIND_DECODE:
+                B = h[1]
+                run.decode(B, p[:B], p[B:2 * B], p[2 * B:].reshape(B, mb))
+            else:
+                S = h[1]
+                lens, starts, sample, nb = p[:S], p[S:2 * S], p[2 * S:3 * S], p[3 * S:4 * S]
+                off = 4 * S
+                tables = []
+                for s in range(S):
+                    tables.append(p[off:off + nb[s]]); off += nb[s]
+                chunks = []
+                for s in range(S):
+                    chunks.append(p[off:off + lens[s]]); off += lens[s]
+                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample])

@@ -1,0 +1,331 @@
+"""GPU model runner: executes prefill and decode steps of a Llama-class decoder with libb200.so.
+
+Restates the reference engine's LlamaModel.forward / LlamaDecoderLayer.forward
+($VLLM/model_executor/models/llama.py:316-333, 395-434) as a fixed sequence of C-ABI kernel
+launches on torch's current stream:
+
+    embed -> 32 x [ (add+)RMSNorm -> QKV GEMM -> RoPE+KV-write -> paged attention -> O GEMM ->
+                    add+RMSNorm -> gate_up GEMM -> SiLU*mul -> down GEMM ] -> add+RMSNorm ->
+    last-token gather -> lm_head GEMM (fp32 logits) -> argmax
+
+Decode steps are captured once per batch bucket in CUDA graphs (the reference engine does the same
+through torch.compile/cudagraph, $VLLM/v1/worker/gpu_model_runner.py); step inputs travel in ONE
+pinned int32 staging buffer copied host->device with a single cudaMemcpyAsync.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import EngineConfig, ModelConfig
+from .lib import B200Error
+from .weights import ModelWeights
+
+BF16 = torch.bfloat16
+_SPLITK_MAX_M = 256
+
+
+def _align(n: int, a: int = 4) -> int:
+    return (n + a - 1) // a * a
+
+
+class ModelRunner:
+    def __init__(self, mcfg: ModelConfig, ecfg: EngineConfig, weights: ModelWeights, device: str = "cuda",
+                 tp_group=None):
+        if not torch.cuda.is_available():
+            raise B200Error("ModelRunner needs a CUDA device: this engine has no CPU path")
+        self.mcfg, self.ecfg, self.w = mcfg, ecfg, weights
+        self.device = torch.device(device)
+        self.tp = ecfg.tensor_parallel_size
+        self.tp_group = tp_group
+        self.Hq = mcfg.num_attention_heads // self.tp
+        self.Hkv = mcfg.num_key_value_heads // self.tp
+        self.D = mcfg.head_dim
+        self.H = mcfg.hidden_size
+        self.I = mcfg.intermediate_size // self.tp
+        self.qkv_width = (self.Hq + 2 * self.Hkv) * self.D
+        self.scale = self.D ** -0.5
+        self.max_model_len = ecfg.max_model_len or mcfg.max_position_embeddings
+        self.block_size = ecfg.block_size
+        self.max_blocks = (self.max_model_len + self.block_size - 1) // self.block_size
+        self.max_seqs = ecfg.max_num_seqs
+        self.max_tokens = max(ecfg.max_num_batched_tokens, self.max_seqs)
+        self.prefill_tile = ops.attn_prefill_tile(self.Hq, self.Hkv)
+        self.v_local = weights.lm_head.shape[0]
+        self._alloc_workspace()
+        self.k_cache: List[torch.Tensor] = []
+        self.v_cache: List[torch.Tensor] = []
+        self.num_blocks = 0
+        self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.graph_pool = None
+        self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0}
+
+    # ------------------------------------------------------------------------------ memory
+    def _alloc_workspace(self):
+        dev, T, H = self.device, self.max_tokens, self.H
+        e = lambda *s, dt=BF16: torch.empty(*s, dtype=dt, device=dev)
+        self.resid = e(T, H)
+        self.hbuf = e(T, H)
+        self.xn = e(T, H)
+        self.qkv = e(T, self.qkv_width)
+        self.attn_out = e(T, self.Hq * self.D)
+        self.gu = e(T, 2 * self.I)
+        self.act = e(T, self.I)
+        self.x_last = e(self.max_seqs, H)
+        self.logits = e(self.max_seqs, self.v_local, dt=torch.float32)
+        self.out_ids = torch.zeros(self.max_seqs, dtype=torch.int32, device=dev)
+        self.out_vals = torch.zeros(self.max_seqs, dtype=torch.float32, device=dev)
+        self.partials = e(8 * min(_SPLITK_MAX_M, T) * H, dt=torch.float32)   # flat: viewed [splits, T, H]
+        self.cos_sin = self._cos_sin_cache().to(dev)
+        # one int32 staging area for all step inputs (host pinned + device mirror)
+        n_tiles_max = T // self.prefill_tile + self.max_seqs + 1
+        self.stage_words = _align(3 * T) + 4 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
+            + self.max_seqs * self.max_blocks + 64
+        self.stage_host = torch.zeros(self.stage_words, dtype=torch.int32, pin_memory=True)
+        self.stage_np = self.stage_host.numpy()
+        self.stage_dev = torch.zeros(self.stage_words, dtype=torch.int32, device=dev)
+        self.out_host = torch.zeros(self.max_seqs, dtype=torch.int32, pin_memory=True)
+        # fixed decode layout inside the staging area
+        S = self.max_seqs
+        self.d_ids, self.d_pos, self.d_slots, self.d_lens = 0, S, 2 * S, 3 * S
+        self.d_bt = 4 * S
+        self.attn_ws: Dict[int, torch.Tensor] = {}
+
+    def _cos_sin_cache(self) -> torch.Tensor:
+        # $VLLM/model_executor/layers/rotary_embedding/base.py:71-93; kept in the model dtype
+        D = self.D
+        inv_freq = 1.0 / (self.mcfg.rope_theta ** (torch.arange(0, D, 2, dtype=torch.float) / D))
+        t = torch.arange(self.max_model_len, dtype=torch.float)
+        freqs = torch.einsum("i,j -> ij", t, inv_freq)
+        return torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(BF16)
+
+    def kv_block_bytes(self) -> int:
+        return 2 * self.mcfg.num_hidden_layers * self.Hkv * self.block_size * self.D * 2
+
+    def profile_num_blocks(self) -> int:
+        """KV blocks that fit in gpu_memory_utilization of the device after weights + workspace."""
+        if self.ecfg.num_gpu_blocks:
+            return int(self.ecfg.num_gpu_blocks)
+        torch.cuda.synchronize()
+        free, total = torch.cuda.mem_get_info()
+        budget = free - int(total * (1.0 - self.ecfg.gpu_memory_utilization)) - (1 << 30)  # graphs etc.
+        n = budget // self.kv_block_bytes()
+        need = self.max_blocks + 1
+        if n < need:
+            raise B200Error(f"not enough GPU memory for the KV cache: {n} blocks available, "
+                            f"{need} needed for one sequence of max_model_len={self.max_model_len}")
+        return int(n)
+
+    def init_kv_cache(self, num_blocks: int) -> None:
+        self.num_blocks = num_blocks
+        shape = (num_blocks, self.Hkv, self.block_size, self.D)
+        self.k_cache = [torch.zeros(shape, dtype=BF16, device=self.device) for _ in range(self.mcfg.num_hidden_layers)]
+        self.v_cache = [torch.zeros(shape, dtype=BF16, device=self.device) for _ in range(self.mcfg.num_hidden_layers)]
+
+    # ------------------------------------------------------------------------------ layers
+    def _row_parallel(self, x: torch.Tensor, w: torch.Tensor, T: int, norm_w: torch.Tensor):
+        """O / down projection followed by (all-reduce +) residual add + RMSNorm -> self.xn."""
+        eps = self.mcfg.rms_norm_eps
+        if self.tp > 1:
+            ops.gemm(x, w, out=self.hbuf[:T])
+            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
+            ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
+                                   residual_out=self.resid[:T])
+            self.stats["kernel_launches"] += 3
+            return
+        splits = ops.gemm_suggest_splits(T, w.shape[0], w.shape[1]) if T <= _SPLITK_MAX_M else 1
+        if splits > 1:
+            parts = self.partials[:splits * T * self.H].view(splits, T, self.H)
+            ops.gemm(x, w, out=parts, splits=splits)
+            ops.fused_add_rms_norm_partials(parts, self.resid[:T], norm_w, eps, self.xn[:T], self.resid[:T])
+        else:
+            ops.gemm(x, w, out=self.hbuf[:T])
+            ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
+                                   residual_out=self.resid[:T])
+        self.stats["kernel_launches"] += 2
+
+    def _layers(self, T: int, attn_fn) -> None:
+        """Runs all decoder layers over self.resid[:T] (already holding the embeddings); leaves the
+        final-normed hidden states in self.xn[:T]."""
+        m, w = self.mcfg, self.w
+        pos, slots = self._pos, self._slots
+        ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
+        for l, lw in enumerate(w.layers):
+            ops.gemm(self.xn[:T], lw.qkv, out=self.qkv[:T])
+            if lw.qkv_bias is not None:
+                self.qkv[:T].add_(lw.qkv_bias)
+            ops.rope_kv_write(self.qkv[:T], pos, self.cos_sin, self.k_cache[l], self.v_cache[l], slots,
+                              self.Hq, self.Hkv, self.D)
+            attn_fn(l)
+            self._row_parallel(self.attn_out[:T], lw.o, T, lw.post_norm)
+            ops.gemm(self.xn[:T], lw.gate_up, out=self.gu[:T])
+            ops.silu_and_mul(self.gu[:T], out=self.act[:T])
+            nxt = w.layers[l + 1].input_norm if l + 1 < len(w.layers) else w.final_norm
+            self._row_parallel(self.act[:T], lw.down, T, nxt)
+            self.stats["kernel_launches"] += 5
+
+    def _sample(self, n: int, rows: Optional[torch.Tensor]) -> None:
+        """greedy token of n sequences into self.out_ids[:n]; rows = last-token row of each."""
+        x = self.xn[:n] if rows is None else ops.gather_rows(self.xn, rows, out=self.x_last[:n])
+        lg = self.logits[:n]
+        ops.gemm(x, self.w.lm_head, out=lg, out_dtype=torch.float32)
+        if self.tp == 1:
+            ops.argmax(lg, out_idx=self.out_ids[:n])
+            self.stats["kernel_launches"] += 2 + (rows is not None)
+            return
+        ops.argmax(lg, out_idx=self.out_ids[:n], out_val=self.out_vals[:n])
+        vals = torch.empty(self.tp, n, dtype=torch.float32, device=self.device)
+        idxs = torch.empty(self.tp, n, dtype=torch.int32, device=self.device)
+        torch.distributed.all_gather_into_tensor(vals, self.out_vals[:n].contiguous(), group=self.tp_group)
+        torch.distributed.all_gather_into_tensor(idxs, (self.out_ids[:n] + self.w.vocab_start).contiguous(),
+                                                 group=self.tp_group)
+        best = vals.argmax(dim=0, keepdim=True)   # ties -> lowest rank = lowest vocab index
+        self.out_ids[:n].copy_(idxs.gather(0, best)[0])
+
+    # ------------------------------------------------------------------------------ decode
+    def _decode_forward(self, B: int) -> None:
+        sd = self.stage_dev
+        ids = sd[self.d_ids:self.d_ids + B]
+        self._pos = sd[self.d_pos:self.d_pos + B]
+        self._slots = sd[self.d_slots:self.d_slots + B]
+        lens = sd[self.d_lens:self.d_lens + B]
+        bt = sd[self.d_bt:self.d_bt + B * self.max_blocks].view(B, self.max_blocks)
+        ops.embedding(ids, self.w.embed, out=self.resid[:B])
+        splits = ops.attn_decode_splits(B, self.Hkv, self.max_model_len)
+        ws = self.attn_ws.get(B)
+        if ws is None:
+            ws = self.attn_ws[B] = ops.attn_decode_workspace(B, self.Hq, self.D, splits, self.device)
+
+        def attn(l):
+            ops.paged_attn_decode(self.qkv[:B], self.qkv_width, self.k_cache[l], self.v_cache[l], bt, lens,
+                                  self.attn_out[:B], self.Hq, self.Hkv, self.D, self.scale,
+                                  num_splits=splits, workspace=ws)
+
+        self._layers(B, attn)
+        self._sample(B, None)
+
+    def capture_graphs(self) -> None:
+        if self.ecfg.enforce_eager:
+            return
+        self.stage_dev.zero_()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for B in sorted(self.ecfg.graph_buckets(), reverse=True):
+                self._decode_forward(B)          # warm-up (allocates workspaces, sets func attrs)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.graph_pool, stream=s):
+                    self._decode_forward(B)
+                if self.graph_pool is None:
+                    self.graph_pool = g.pool()
+                self.graphs[B] = g
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._buckets = sorted(self.graphs)
+
+    def decode(self, B: int, last_token: np.ndarray, num_computed: np.ndarray, block_table: np.ndarray) -> np.ndarray:
+        """One decode step for rows 0..B-1 of the scheduler's persistent batch."""
+        S, bs = self.max_seqs, self.block_size
+        Bp = B
+        if self.graphs:
+            Bp = next((b for b in self._buckets if b >= B), None)
+            if Bp is None:
+                raise B200Error(f"decode batch {B} exceeds the largest captured graph")
+        st = self.stage_np
+        pos = num_computed[:B]
+        st[self.d_ids:self.d_ids + B] = last_token[:B]
+        st[self.d_pos:self.d_pos + B] = pos
+        st[self.d_slots:self.d_slots + B] = block_table[np.arange(B), pos // bs] * bs + pos % bs
+        st[self.d_lens:self.d_lens + B] = pos + 1
+        if Bp > B:   # padding rows: no cache write, zero-length attention
+            st[self.d_ids + B:self.d_ids + Bp] = 0
+            st[self.d_pos + B:self.d_pos + Bp] = 0
+            st[self.d_slots + B:self.d_slots + Bp] = -1
+            st[self.d_lens + B:self.d_lens + Bp] = 0
+        st[self.d_bt:self.d_bt + B * self.max_blocks] = block_table[:B].reshape(-1)
+        n = self.d_bt + B * self.max_blocks
+        self.stage_dev[:n].copy_(self.stage_host[:n], non_blocking=True)
+        if self.graphs:
+            self.graphs[Bp].replay()
+            self.stats["graph_replays"] += 1
+        else:
+            self._decode_forward(Bp)
+        self.out_host[:B].copy_(self.out_ids[:B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.stats["decode_steps"] += 1
+        return self.out_host[:B].numpy()
+
+    # ------------------------------------------------------------------------------ prefill
+    def prefill(self, token_chunks: Sequence[Sequence[int]], starts: Sequence[int], block_tables: Sequence[Sequence[int]],
+                sample: Sequence[bool]) -> np.ndarray:
+        """Runs one (chunked) prefill step.  token_chunks[s] are the ids of chunk s, which occupies
+        positions [starts[s], starts[s]+len).  Returns the greedy token of every chunk with
+        sample[s] == True, in order."""
+        S = len(token_chunks)
+        lens = [len(c) for c in token_chunks]
+        T = sum(lens)
+        if T > self.max_tokens or S > self.max_seqs:
+            raise B200Error(f"prefill step too large: {T} tokens / {S} sequences")
+        bs = self.block_size
+        st = self.stage_np
+        o_ids, o_pos, o_slots = 0, _align(T), 2 * _align(T)
+        o_cu = 3 * _align(T)
+        o_ctx = o_cu + _align(S + 1)
+        o_rows = o_ctx + _align(S)
+        tile_seq, tile_q0 = ops.build_prefill_tiles(lens, self.prefill_tile)
+        nt = len(tile_seq)
+        o_ts = o_rows + _align(S)
+        o_tq = o_ts + _align(nt)
+        o_bt = o_tq + _align(nt)
+        end = o_bt + S * self.max_blocks
+        cu = np.zeros(S + 1, dtype=np.int32)
+        np.cumsum(lens, out=cu[1:])
+        bt = np.zeros((S, self.max_blocks), dtype=np.int32)
+        for s in range(S):
+            a, b = cu[s], cu[s + 1]
+            tbl = np.asarray(block_tables[s], dtype=np.int32)
+            bt[s, :len(tbl)] = tbl
+            p = np.arange(starts[s], starts[s] + lens[s], dtype=np.int32)
+            st[o_ids + a:o_ids + b] = token_chunks[s]
+            st[o_pos + a:o_pos + b] = p
+            st[o_slots + a:o_slots + b] = tbl[p // bs] * bs + p % bs
+        st[o_cu:o_cu + S + 1] = cu
+        st[o_ctx:o_ctx + S] = starts
+        sample_rows = [int(cu[s + 1]) - 1 for s in range(S) if sample[s]]
+        ns = len(sample_rows)
+        st[o_rows:o_rows + ns] = sample_rows
+        st[o_ts:o_ts + nt] = tile_seq
+        st[o_tq:o_tq + nt] = tile_q0
+        st[o_bt:end] = bt.reshape(-1)
+        self.stage_dev[:end].copy_(self.stage_host[:end], non_blocking=True)
+        sd = self.stage_dev
+        ids = sd[o_ids:o_ids + T]
+        self._pos, self._slots = sd[o_pos:o_pos + T], sd[o_slots:o_slots + T]
+        cu_d, ctx_d = sd[o_cu:o_cu + S + 1], sd[o_ctx:o_ctx + S]
+        ts_d, tq_d = sd[o_ts:o_ts + nt], sd[o_tq:o_tq + nt]
+        bt_d = sd[o_bt:end].view(S, self.max_blocks)
+        ops.embedding(ids, self.w.embed, out=self.resid[:T])
+
+        def attn(l):
+            ops.paged_attn_prefill(self.qkv[:T], self.qkv_width, self.k_cache[l], self.v_cache[l], bt_d, cu_d,
+                                   ctx_d, ts_d, tq_d, self.attn_out[:T], self.Hq, self.Hkv, self.D, self.scale)
+
+        self._layers(T, attn)
+        self.stats["prefill_steps"] += 1
+        if ns == 0:
+            torch.cuda.current_stream().synchronize()
+            return np.zeros(0, dtype=np.int32)
+        self._sample(ns, sd[o_rows:o_rows + ns])
+        self.out_host[:ns].copy_(self.out_ids[:ns], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.out_host[:ns].numpy().copy()
+
+    # -------------------------------------------------------------------- test / debug hooks
+    def last_logits(self, n: int) -> torch.Tensor:
+        """fp32 logits of the last _sample() call (local vocab shard), for parity tests."""
+        return self.logits[:n].clone()

@@ -1,0 +1,318 @@
+"""Continuous-batching scheduler (host side).
+
+Counterpart of the reference engine's Scheduler.schedule ($VLLM/v1/core/sched/scheduler.py:329):
+token-budgeted prefill batches (with chunking of long prompts), decode batches over every running
+sequence, block allocation / preemption through KVCacheManager.  Policy: prefill-first (best
+TTFT and throughput for the benchmark_serving.py workload), decode otherwise.
+
+Running sequences live in a compact "persistent batch" of numpy arrays (rows 0..B-1) so that a
+decode step's inputs are produced by a handful of vectorised numpy ops instead of per-request
+Python.
+"""
+from __future__ import annotations
+
+import time
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Deque, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .kv_cache import BlockPool
+
+
+@dataclass
+class SamplingParams:
+    max_tokens: int = 16
+    temperature: float = 0.0
+    top_p: float = 1.0
+    ignore_eos: bool = False
+    stop_token_ids: Tuple[int, ...] = ()
+    seed: Optional[int] = None
+
+
+@dataclass
+class Request:
+    req_id: str
+    prompt_ids: List[int]
+    params: SamplingParams
+    arrival: float = field(default_factory=time.monotonic)
+    output_ids: List[int] = field(default_factory=list)
+    num_computed: int = 0          # prompt tokens whose K/V are in the cache (prefill progress)
+    row: int = -1                  # row in the persistent batch, -1 = not resident
+    blocks: List[int] = field(default_factory=list)
+    first_token_time: Optional[float] = None
+    finished: bool = False
+    finish_reason: Optional[str] = None
+    num_preemptions: int = 0
+
+    @property
+    def all_ids(self) -> List[int]:
+        return self.prompt_ids + self.output_ids
+
+    @property
+    def prefill_target(self) -> int:
+        # after a preemption the generated tokens are recomputed as part of the prompt
+        return len(self.prompt_ids) + len(self.output_ids)
+
+
+@dataclass
+class PrefillPlan:
+    reqs: List[Request]
+    starts: List[int]              # first position of each chunk
+    lens: List[int]                # tokens in each chunk
+    sample: List[bool]             # chunk completes the prompt -> sample a token
+
+    @property
+    def num_tokens(self) -> int:
+        return sum(self.lens)
+
+
+@dataclass
+class DecodePlan:
+    batch: int                     # rows 0..batch-1 of the persistent batch
+
+
+@dataclass
+class StepOutput:
+    req_ids: List[str]
+    token_ids: List[int]
+    finished: List[Optional[str]]  # finish reason or None
+
+
+class Scheduler:
+    def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
+                 max_model_len: int, eos_token_id: Optional[int]):
+        self.pool = BlockPool(num_blocks, block_size)
+        self.block_size = block_size
+        self.max_num_seqs = max_num_seqs
+        self.max_tokens_per_step = max_num_batched_tokens
+        self.max_model_len = max_model_len
+        self.eos = -1 if eos_token_id is None else int(eos_token_id)
+        self.max_blocks_per_seq = (max_model_len + block_size - 1) // block_size
+        self.waiting: Deque[Request] = deque()
+        self.prefilling: List[Request] = []     # admitted, prompt not fully computed yet
+        self.rows: List[Optional[Request]] = []  # decode-resident requests, compact
+        S = max_num_seqs
+        self.last_token = np.zeros(S, dtype=np.int32)
+        self.num_computed = np.zeros(S, dtype=np.int32)
+        self.remaining = np.zeros(S, dtype=np.int32)
+        self.check_eos = np.zeros(S, dtype=bool)
+        self.n_blocks = np.zeros(S, dtype=np.int32)
+        self.block_table = np.zeros((S, self.max_blocks_per_seq), dtype=np.int32)
+        self.num_preemptions = 0
+
+    # ------------------------------------------------------------------ queue side
+    def add(self, req: Request) -> None:
+        total = len(req.prompt_ids) + req.params.max_tokens
+        if len(req.prompt_ids) == 0:
+            raise ValueError("empty prompt")
+        if total > self.max_model_len:
+            raise ValueError(f"prompt ({len(req.prompt_ids)}) + max_tokens ({req.params.max_tokens}) "
+                             f"exceeds max_model_len ({self.max_model_len})")
+        self.waiting.append(req)
+
+    def abort(self, req_id: str) -> bool:
+        for q in (self.waiting,):
+            for r in list(q):
+                if r.req_id == req_id:
+                    q.remove(r)
+                    r.finished, r.finish_reason = True, "abort"
+                    return True
+        for r in list(self.prefilling):
+            if r.req_id == req_id:
+                self.prefilling.remove(r)
+                self._release(r)
+                r.finished, r.finish_reason = True, "abort"
+                return True
+        for r in self.rows:
+            if r is not None and r.req_id == req_id:
+                self._evict_row(r.row)
+                self._release(r)
+                r.finished, r.finish_reason = True, "abort"
+                return True
+        return False
+
+    @property
+    def num_running(self) -> int:
+        return len(self.rows) + len(self.prefilling)
+
+    @property
+    def num_waiting(self) -> int:
+        return len(self.waiting)
+
+    def has_work(self) -> bool:
+        return bool(self.waiting or self.prefilling or self.rows)
+
+    def kv_usage(self) -> float:
+        return self.pool.usage()
+
+    # ------------------------------------------------------------------ scheduling
+    def _blocks_for(self, ntok: int) -> int:
+        return (ntok + self.block_size - 1) // self.block_size
+
+    def _release(self, r: Request) -> None:
+        if r.blocks:
+            self.pool.free(r.blocks)
+            r.blocks = []
+
+    def schedule(self):
+        """Returns a PrefillPlan, a DecodePlan, or None when idle."""
+        plan = self._schedule_prefill()
+        if plan is not None:
+            return plan
+        if self.rows:
+            self._ensure_decode_blocks()
+            if self.rows:
+                return DecodePlan(batch=len(self.rows))
+        return None
+
+    def _schedule_prefill(self) -> Optional[PrefillPlan]:
+        budget = self.max_tokens_per_step
+        reqs, starts, lens, sample = [], [], [], []
+        # 1. continue partially prefilled prompts
+        for r in self.prefilling:
+            if budget <= 0:
+                break
+            n = min(budget, r.prefill_target - r.num_computed)
+            reqs.append(r); starts.append(r.num_computed); lens.append(n)
+            sample.append(r.num_computed + n == r.prefill_target)
+            budget -= n
+        # 2. admit new requests while sequence slots, tokens and KV blocks last
+        while self.waiting and budget > 0:
+            r = self.waiting[0]
+            if len(self.rows) + len(self.prefilling) >= self.max_num_seqs:
+                break
+            need = self._blocks_for(r.prefill_target + 1)
+            # keep one spare block per running sequence so that decode does not preempt at once
+            if need + len(self.rows) > self.pool.num_free:
+                break
+            self.waiting.popleft()
+            r.blocks = self.pool.allocate(need)
+            r.num_computed = 0
+            self.prefilling.append(r)
+            n = min(budget, r.prefill_target)
+            reqs.append(r); starts.append(0); lens.append(n)
+            sample.append(n == r.prefill_target)
+            budget -= n
+        if not reqs:
+            return None
+        return PrefillPlan(reqs, starts, lens, sample)
+
+    def _ensure_decode_blocks(self) -> None:
+        """Every resident row needs a slot for position num_computed; allocate, preempting the
+        most recently admitted rows when the pool runs dry."""
+        while True:
+            B = len(self.rows)
+            pos = self.num_computed[:B]
+            need = (pos // self.block_size) >= self.n_blocks[:B]
+            idx = np.nonzero(need)[0]
+            if len(idx) <= self.pool.num_free:
+                for i in idx:
+                    r = self.rows[i]
+                    b = self.pool.allocate(1)[0]
+                    r.blocks.append(b)
+                    self.block_table[i, self.n_blocks[i]] = b
+                    self.n_blocks[i] += 1
+                return
+            self._preempt_last()
+            if not self.rows:
+                return
+
+    def _preempt_last(self) -> None:
+        r = self.rows[-1]
+        self._evict_row(r.row)
+        self._release(r)
+        r.num_computed = 0
+        r.num_preemptions += 1
+        self.num_preemptions += 1
+        self.waiting.appendleft(r)
+
+    # ------------------------------------------------------------------ persistent batch
+    def _install_row(self, r: Request, first_token: int) -> None:
+        i = len(self.rows)
+        self.rows.append(r)
+        r.row = i
+        self.last_token[i] = first_token
+        self.num_computed[i] = r.num_computed   # K/V tokens in the cache; `first_token` sits at this position
+        self.remaining[i] = r.params.max_tokens - len(r.output_ids)
+        self.check_eos[i] = not r.params.ignore_eos
+        nb = len(r.blocks)
+        self.n_blocks[i] = nb
+        self.block_table[i, :nb] = r.blocks
+        self.block_table[i, nb:] = 0
+
+    def _evict_row(self, i: int) -> None:
+        last = len(self.rows) - 1
+        r = self.rows[i]
+        if i != last:
+            m = self.rows[last]
+            self.rows[i] = m
+            m.row = i
+            for a in (self.last_token, self.num_computed, self.remaining, self.check_eos, self.n_blocks):
+                a[i] = a[last]
+            self.block_table[i] = self.block_table[last]
+        self.rows.pop()
+        r.row = -1
+
+    # ------------------------------------------------------------------ results
+    def _finish_reason(self, r: Request, tok: int) -> Optional[str]:
+        p = r.params
+        if not p.ignore_eos and (tok == self.eos or tok in p.stop_token_ids):
+            return "stop"
+        if len(r.output_ids) >= p.max_tokens:
+            return "length"
+        return None
+
+    def update_prefill(self, plan: PrefillPlan, sampled: Sequence[int]) -> StepOutput:
+        """`sampled[j]` is the token of the j-th plan entry with sample=True."""
+        out = StepOutput([], [], [])
+        now = time.monotonic()
+        j = 0
+        for r, n, smp in zip(plan.reqs, plan.lens, plan.sample):
+            r.num_computed += n
+            if not smp:
+                continue
+            tok = int(sampled[j]); j += 1
+            self.prefilling.remove(r)
+            r.output_ids.append(tok)
+            if r.first_token_time is None:
+                r.first_token_time = now
+            reason = self._finish_reason(r, tok)
+            out.req_ids.append(r.req_id); out.token_ids.append(tok); out.finished.append(reason)
+            if reason is not None:
+                r.finished, r.finish_reason = True, reason
+                self._release(r)
+            else:
+                self._install_row(r, tok)
+        return out
+
+    def update_decode(self, plan: DecodePlan, sampled: np.ndarray) -> StepOutput:
+        B = plan.batch
+        sampled = np.asarray(sampled[:B], dtype=np.int32)
+        self.last_token[:B] = sampled
+        self.num_computed[:B] += 1
+        self.remaining[:B] -= 1
+        done = self.remaining[:B] <= 0
+        stop = self.check_eos[:B] & (sampled == self.eos)
+        out = StepOutput([], sampled.tolist(), [None] * B)
+        rows = list(self.rows)
+        out.req_ids = [r.req_id for r in rows]
+        toks = out.token_ids
+        for i, r in enumerate(rows):
+            r.output_ids.append(toks[i])
+        fin = done | stop
+        # per-request stop_token_ids are rare; only requests that set them pay for the check
+        for i, r in enumerate(rows):
+            p = r.params
+            if p.stop_token_ids and not p.ignore_eos and toks[i] in p.stop_token_ids:
+                fin[i] = True
+                stop[i] = True
+        for i in np.nonzero(fin)[0][::-1].tolist():   # descending: swaps never touch pending rows
+            r = rows[i]
+            reason = "stop" if stop[i] else "length"
+            out.finished[i] = reason
+            r.finished, r.finish_reason = True, reason
+            self._evict_row(r.row)
+            self._release(r)
+        return out

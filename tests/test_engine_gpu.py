@@ -1,0 +1,98 @@
+"""End-to-end parity of the engine (scheduler + runner + kernels) against the CPU oracle on the
+seeded tiny Llama configs.  Stated tolerance: last-position logits
+max-abs-diff <= 2e-2 * max|logit|; greedy tokens teacher-forced: wherever the oracle's top-2
+margin exceeds that tolerance the engine must pick the same token."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cfg_o, seed=7, **kw):
+    from gpustack_b200.config import EngineConfig, ModelConfig
+    from gpustack_b200.engine import LLMEngine
+
+    mcfg = ModelConfig(vocab_size=cfg_o.vocab_size, hidden_size=cfg_o.hidden_size,
+                       intermediate_size=cfg_o.intermediate_size, num_hidden_layers=cfg_o.num_hidden_layers,
+                       num_attention_heads=cfg_o.num_attention_heads, num_key_value_heads=cfg_o.num_key_value_heads,
+                       head_dim=cfg_o.head_dim, rms_norm_eps=cfg_o.rms_norm_eps, rope_theta=cfg_o.rope_theta,
+                       max_position_embeddings=cfg_o.max_position_embeddings, eos_token_id=2)
+    weights = O.init_weights(cfg_o, seed=seed)
+    ecfg = EngineConfig(max_num_seqs=kw.pop("max_num_seqs", 16), max_num_batched_tokens=kw.pop("mbt", 256),
+                        num_gpu_blocks=kw.pop("blocks", 128), **kw)
+    eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
+    return eng, O.OracleLlama(cfg_o, weights)
+
+
+@pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128], ids=["tiny64", "tiny128"])
+@pytest.mark.parametrize("eager", [True, False], ids=["eager", "graphs"])
+def test_prefill_logits_and_greedy_decode(cfg_o, eager):
+    from gpustack_b200.scheduler import SamplingParams
+
+    eng, oracle = _engine(cfg_o, enforce_eager=eager, cuda_graph_sizes=[1, 2, 4, 8])
+    g = torch.Generator().manual_seed(11)
+    prompts = [torch.randint(3, cfg_o.vocab_size, (n,), generator=g).tolist() for n in (5, 23, 64, 100, 17)]
+    # 1) prefill logits of the last prompt position
+    eng.add_request("p0", prompts[1], SamplingParams(max_tokens=1, ignore_eos=True))
+    out = eng.step()
+    got = eng.runner.last_logits(1)[0].cpu()
+    ref = oracle.forward(0, prompts[1])[-1]
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 2e-2 * scale
+    assert out.finished == ["length"]
+    oracle.reset()
+    # 2) continuous batching, greedy, teacher-forced comparison
+    N = 24
+    outs = eng.generate(prompts, SamplingParams(max_tokens=N, ignore_eos=True))
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        assert len(o) == N
+        oracle.reset()
+        logits = oracle.forward(i, p)[-1]
+        n_checked = 0
+        for t in range(N):
+            top2 = torch.topk(logits, 2).values
+            margin = float(top2[0] - top2[1])
+            if margin > 2e-2 * float(logits.abs().max()):
+                assert int(torch.argmax(logits)) == o[t], f"seq {i} step {t}: margin {margin}"
+                n_checked += 1
+            logits = oracle.forward(i, [o[t]])[-1]     # teacher forcing with the engine's token
+        assert n_checked >= N // 3
+
+
+def test_chunked_prefill_and_preemption_match_unchunked():
+    """A prompt longer than the token budget is prefilled in chunks; a tiny KV pool forces
+    preemption + recompute.  Outputs must equal the roomy single-shot run (same kernels, greedy)."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    g = torch.Generator().manual_seed(5)
+    prompts = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (300, 40, 150, 90)]
+    sp = SamplingParams(max_tokens=20, ignore_eos=True)
+    eng_a, _ = _engine(O.TINY, mbt=512, blocks=256, enforce_eager=True)
+    ref = eng_a.generate(prompts, sp)
+    del eng_a
+    eng_b, _ = _engine(O.TINY, mbt=64, blocks=50, enforce_eager=True, max_num_seqs=4)
+    got = eng_b.generate(prompts, sp)
+    assert eng_b.runner.stats["prefill_steps"] > 4
+    # chunking changes the reduction order inside attention only marginally; tokens must agree
+    # except at near-ties, so require >= 90% positional agreement and identical first tokens
+    for a, b in zip(ref, got):
+        assert a[0] == b[0]
+        agree = sum(x == y for x, y in zip(a, b)) / len(a)
+        assert agree >= 0.9 or a[: len(a) // 2] == b[: len(b) // 2]
+
+
+def test_eos_and_stop_handling():
+    from gpustack_b200.scheduler import SamplingParams
+
+    eng, oracle = _engine(O.TINY, enforce_eager=True)
+    g = torch.Generator().manual_seed(2)
+    p = torch.randint(3, 500, (12,), generator=g).tolist()
+    free_run = eng.generate([p], SamplingParams(max_tokens=10, ignore_eos=True))[0]
+    stop_tok = free_run[3]
+    stopped = eng.generate([p], SamplingParams(max_tokens=10, stop_token_ids=(stop_tok,)))[0]
+    first = free_run.index(stop_tok)
+    assert stopped == free_run[: first + 1]
+    assert eng.sched.pool.num_free == eng.sched.pool.num_total   # every block returned
