@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the hot path: output tok/s (+ p50 TTFT) of
+continuous-batched Llama-3-8B bf16 serving, 512-token prompts / 128 greedy output tokens
+(BASELINE.json configs[1]; TP = --gpus), random-init weights, synthetic token-id prompts.
+
+  python bench.py --gpus 1 --steps K --warmup W                      (this engine)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W     (tensor parallel, 1 rank/GPU)
+  python bench.py --impl reference ...                               (CPU restatement on host cores)
+
+A "step" = one pass of the workload: R requests (default 256) admitted at once, run to completion
+by the continuous-batching engine.  `value` is measured on the engine core (device-timed, max over
+ranks); `e2e` is the same metric through the reference-facing boundary: the OpenAI HTTP server
+(/v1/completions, SSE streaming) driven by a separate client process with the TTFT / output-tok/s
+definitions of the reference's benchmarks/benchmark_serving.py.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "output_tok_per_s"
+UNIT = "tok/s"
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--requests", type=int, default=256, help="requests per step (= concurrency)")
+    ap.add_argument("--input-len", type=int, default=512)
+    ap.add_argument("--output-len", type=int, default=128)
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tiny", "tiny128"])
+    ap.add_argument("--no-e2e", action="store_true", help="skip the HTTP end-to-end leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-requests", type=int, default=2)
+    ap.add_argument("--cpu-sample-output", type=int, default=16)
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def host_threads() -> int:
+    """Usable host cores: min(affinity, cgroup CPU quota).  (The GPU boxes expose 128 logical CPUs
+    but cap the container at 16 via cpu.max; asking torch for 128 threads there is pathological.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def model_config(name):
+    from gpustack_b200.config import llama3_8b, tiny_llama
+
+    return {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128)}[name]()
+
+
+def workload(step, R, in_len, vocab):
+    import numpy as np
+
+    rs = np.random.RandomState(1000 + step)
+    lo = 256 if vocab > 1024 else 3
+    return rs.randint(lo, vocab - lo, size=(R, in_len)).tolist()
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- CPU baseline / reference
+def cpu_reference(mname, n_req, in_len, out_len, state_cpu=None):
+    """Times the CPU restatement of the path (oracle/llama_oracle.py: PyTorch fp32 over the same
+    bf16 weights, all host cores) on a bounded sample: n_req requests, run one after another,
+    each a full prefill + greedy decode with KV history.  Returns (tok/s, p50 TTFT ms, seconds)."""
+    import torch
+
+    from oracle import llama_oracle as O
+
+    cfg = {"llama3-8b": O.LLAMA3_8B, "tiny": O.TINY, "tiny128": O.TINY128}[mname]
+    torch.set_num_threads(host_threads())
+    if state_cpu is None:
+        # values are irrelevant for timing; uniform fill is much faster than randn for 8B params
+        state_cpu = {}
+        g = torch.Generator().manual_seed(0)
+        base = O.init_weights(O.LlamaConfig(**{**cfg.__dict__, "num_hidden_layers": 1}), seed=0)
+        for l in range(cfg.num_hidden_layers):
+            for k, v in base.items():
+                if k.startswith("model.layers.0."):
+                    state_cpu[k.replace("layers.0.", f"layers.{l}.")] = v.clone()
+        for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
+            if k in base:
+                state_cpu[k] = base[k]
+    model = O.OracleLlama(cfg, state_cpu, fp32_cache=True)
+    prompts = workload(9999, n_req, in_len, cfg.vocab_size)
+    ttfts, toks = [], 0
+    t0 = time.perf_counter()
+    for i, p in enumerate(prompts):
+        ts = time.perf_counter()
+        logits = model.forward(i, p, last_only=True)[-1]
+        nxt = int(torch.argmax(logits))
+        ttfts.append((time.perf_counter() - ts) * 1e3)
+        toks += 1
+        for _ in range(out_len - 1):
+            logits = model.forward(i, [nxt], last_only=True)[-1]
+            nxt = int(torch.argmax(logits))
+            toks += 1
+        model.kv.pop(i, None)
+    dt = time.perf_counter() - t0
+    return toks / dt, statistics.median(ttfts), dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    vals, ttf, secs = [], [], 0.0
+    n_req, out_len = max(1, a.cpu_sample_requests), a.cpu_sample_output
+    for k in range(a.warmup + a.steps):
+        v, t, dt = cpu_reference(a.model, n_req if k >= a.warmup else 1, a.input_len, out_len if k >= a.warmup else 2)
+        if k >= a.warmup:
+            vals.append(v); ttf.append(t); secs += dt
+    value = statistics.mean(vals)
+    cores = torch.get_num_threads()
+    sample = f"{n_req} requests x {a.input_len} in / {out_len} out per step, sequential, KV history on host"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16 weights / fp32 math", "data": "synthetic",
+        "config": {"workload": f"{a.model} {a.input_len}-in/{a.output_len}-out greedy (bounded CPU sample)",
+                   "requests_per_step": n_req},
+        "p50_ttft_ms": statistics.median(ttf),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "llama-box / llama.cpp are absent offline; this is oracle/llama_oracle.py on host cores",
+    }))
+
+
+# ------------------------------------------------------------------------------------ ours
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_http_leg(engine, a, mcfg, n_warm, n_timed):
+    """Serve the SAME engine over HTTP from this process (uvicorn thread + engine-core thread) and
+    drive it from a separate client process."""
+    import uvicorn
+
+    from gpustack_b200.async_engine import AsyncEngine
+    from gpustack_b200.server import create_app
+    from gpustack_b200.tokenizer import load_tokenizer
+
+    tok = load_tokenizer(None, mcfg.vocab_size, mcfg.bos_token_id, mcfg.eos_token_id)
+    aeng = AsyncEngine(engine)
+    app = create_app(aeng, tok, "bench-model", engine.ecfg.max_model_len)
+    port = free_port()
+    server = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=port, log_level="error", access_log=False,
+                                           backlog=4096))
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    for _ in range(200):
+        if server.started:
+            break
+        time.sleep(0.05)
+    st0 = None
+    out = []
+    try:
+        cmd = [sys.executable, "-m", "gpustack_b200.bench_client", "--url", f"http://127.0.0.1:{port}", "--model",
+               "bench-model", "-n", str(a.requests), "-c", str(a.requests), "--input-len", str(a.input_len),
+               "--output-len", str(a.output_len), "--vocab", str(mcfg.vocab_size)]
+        if n_warm:
+            subprocess.run(cmd + ["--seed", "5000", "--repeat", str(n_warm)], check=True, capture_output=True,
+                           cwd=str(ROOT), timeout=600)
+            log("http warm-up done")
+        st0 = dict(engine.runner.stats)
+        r = subprocess.run(cmd + ["--seed", "6000", "--repeat", str(n_timed)], check=True, capture_output=True,
+                           text=True, cwd=str(ROOT), timeout=900)
+        out = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    finally:
+        server.should_exit = True
+        th.join(timeout=10)
+        aeng._stop = True
+        aeng._wake.set()
+        aeng._thread.join(timeout=10)
+    st1 = engine.runner.stats
+    comp = sum(o["completion_tokens"] for o in out)
+    tt = sum(o["total_time_s"] for o in out)
+    ttft = [o["ttft_ms_p50"] for o in out if o["ttft_ms_p50"] is not None]
+    return {
+        "value": comp / tt if tt else 0.0, "unit": UNIT,
+        "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // max(1, n_timed),
+        "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // max(1, n_timed),
+        "p50_ttft_ms": statistics.median(ttft) if ttft else None,
+        "p99_ttft_ms": max((o["ttft_ms_p99"] or 0) for o in out) if out else None,
+        "successful_requests": sum(o["successful"] for o in out), "requests": sum(o["requests"] for o in out),
+        "path": "HTTP /v1/completions SSE, client in a separate process (host JSON in, host text out)",
+    }
+
+
+def run_ours(a):
+    import torch
+
+    from gpustack_b200 import ops
+    from gpustack_b200.config import EngineConfig
+    from gpustack_b200.engine import LLMEngine, TPWorker
+    from gpustack_b200.scheduler import SamplingParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} needs one process per GPU (WORLD_SIZE={world}); launch with "
+                         "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    mcfg = model_config(a.model)
+    ecfg = EngineConfig(model=f"random:{a.model}", tensor_parallel_size=a.gpus, max_num_seqs=a.requests,
+                        max_num_batched_tokens=8192,
+                        max_model_len=min(mcfg.max_position_embeddings, max(1024, a.input_len + a.output_len + 16)),
+                        seed=0)
+    t_init = time.perf_counter()
+    engine = LLMEngine.from_engine_config(ecfg, mcfg=mcfg)
+    init_s = time.perf_counter() - t_init
+    log(f"rank {rank}: engine ready in {init_s:.1f}s, {engine.num_blocks} KV blocks, graphs {len(engine.runner.graphs)}")
+    if rank != 0:
+        TPWorker(engine).serve_forever()
+        return
+    sp = SamplingParams(max_tokens=a.output_len, ignore_eos=True)
+    R, K, W = a.requests, a.steps, a.warmup
+
+    for k in range(W):
+        tw = time.perf_counter()
+        engine.generate(workload(k, R, a.input_len, mcfg.vocab_size), sp)
+        log(f"warm-up step {k}: {time.perf_counter() - tw:.2f}s  step_time={engine.step_time}")
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    st0 = dict(engine.runner.stats)
+    stime0 = dict(engine.step_time)
+    ops.TIMER = ops.KernelTimer()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    engine.sync_mark()
+    e0.record()
+    n_out = 0
+    for k in range(K):
+        outs = engine.generate(workload(W + k, R, a.input_len, mcfg.vocab_size), sp)
+        n_out += sum(len(o) for o in outs)
+    e1.record()
+    engine.sync_mark()
+    elapsed = engine.max_elapsed()
+    ev_ms = e0.elapsed_time(e1)
+    log(f"timed region: {K} steps in {elapsed:.2f}s -> {n_out / elapsed:.0f} tok/s")
+    clk = clocks.stop()
+    timer = ops.TIMER.summary()
+    ops.TIMER = None
+    st1, stime1 = engine.runner.stats, engine.step_time
+    value = n_out / elapsed
+    pk = peaks()
+
+    # ---- roofline of the dominant kernel (prefill-shaped tcgen05 GEMM), timed live with CUDA events
+    gp = timer.get("gemm_prefill", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+    gd = timer.get("gemm_decode", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+    ach = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] else 0.0
+    roofline = {"kernel": "gemm_bf16_tcgen05_kernel<256> (prefill projections)", "bound": "tensor",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "launches": gp["launches"],
+                "avg_launch_ms": gp["ms"] / max(1, gp["launches"]), "share_of_step": gp["ms"] / ev_ms,
+                "peak_source": f"{pk['source']} (sustained cuBLAS bf16)"}
+    # ---- decode phase as a whole against the HBM roofline (weights + KV streamed per step)
+    dsteps = st1["decode_steps"] - st0["decode_steps"]
+    dtime = stime1["decode"] - stime0["decode"]
+    kv_tok = st1["decode_kv_tokens"] - st0["decode_kv_tokens"]
+    dbytes = dsteps * mcfg.weight_bytes(a.gpus) + kv_tok * mcfg.kv_bytes_per_token(a.gpus)
+    dgbs = dbytes / dtime / 1e9 if dtime else 0.0
+    decode_roof = {"bound": "hbm", "achieved": dgbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": dgbs / pk["hbm_gbs"], "steps": dsteps, "ms_per_decode_step": dtime / max(1, dsteps) * 1e3,
+                   "note": "whole decode steps (host-timed incl. launch+sync), algorithmic bytes = weights + KV read"}
+    ptime = stime1["prefill"] - stime0["prefill"]
+    ptok = st1["prefill_tokens"] - st0["prefill_tokens"]
+
+    res = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+        "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Llama-3-8B bf16 TP={a.gpus}, continuous batching, {a.input_len}-in/{a.output_len}-out greedy"
+                   if a.model == "llama3-8b" else f"{a.model} TP={a.gpus} {a.input_len}-in/{a.output_len}-out",
+                   "requests_per_step": R, "concurrency": R, "weights": "seeded N(0,0.02) random init",
+                   "prompts": "seeded uniform token ids, fresh per step (working set 16 GB weights >> 126 MB L2)",
+                   "parallelism": f"tp{a.gpus}", "max_num_batched_tokens": 8192,
+                   "inputs": "token ids staged through one pinned buffer per engine step"},
+        "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
+        "clocks": clk, "roofline": roofline, "decode_roofline": decode_roof,
+        "phase_ms_per_step": {"prefill": ptime / K * 1e3, "decode": dtime / K * 1e3,
+                              "prefill_tok_s": ptok / ptime if ptime else None},
+        "gemm_decode_live": {"launches": gd["launches"], "ms": gd["ms"],
+                             "gbs": gd["bytes"] / (gd["ms"] * 1e-3) / 1e9 if gd["ms"] else None},
+        "event_ms_total": ev_ms, "init_s": init_s, "kv_blocks": engine.num_blocks,
+    }
+    if not a.no_e2e:
+        try:
+            log("HTTP end-to-end leg ...")
+            res["e2e"] = run_http_leg(engine, a, mcfg, n_warm=min(W, 2), n_timed=K)
+            res["p50_ttft_ms"] = res["e2e"]["p50_ttft_ms"]
+            log(f"e2e: {res['e2e']}")
+        except Exception as e:  # noqa: BLE001
+            res["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
+    engine.shutdown()
+    if a.gpus == 1 and not a.no_cpu_baseline:
+        del engine
+        torch.cuda.empty_cache()
+        log("CPU baseline (oracle port) ...")
+        v, t, dt = cpu_reference(a.model, a.cpu_sample_requests, a.input_len, a.cpu_sample_output)
+        log(f"cpu baseline {v:.2f} tok/s in {dt:.1f}s")
+        res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "p50_ttft_ms": t,
+                               "sample": f"{a.cpu_sample_requests} requests x {a.input_len} in / {a.cpu_sample_output} out, "
+                                         f"sequential, {dt:.1f} s of CPU work (oracle/llama_oracle.py, fp32 math)"}
+    print(json.dumps(res))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

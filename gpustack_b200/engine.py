@@ -21,7 +21,7 @@ from .runner import ModelRunner
 from .scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
 from .weights import ModelWeights, load_safetensors_dir, random_state_dict, shard_state_dict
 
-_KIND_STOP, _KIND_DECODE, _KIND_PREFILL = 0, 1, 2
+_KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED = 0, 1, 2, 3, 4
 
 
 class TPContext:
@@ -175,6 +175,33 @@ class LLMEngine:
         if self.tp and self.tp.rank == 0:
             self.tp.bcast_step([_KIND_STOP], None)
 
+    # ------------------------------------------------------------------ timing helpers (bench.py)
+    def sync_mark(self) -> float:
+        """Device-synchronise every rank, barrier, and remember the time (rank 0 drives)."""
+        if self.tp and self.tp.rank == 0:
+            self.tp.bcast_step([_KIND_SYNC], None)
+        return self._do_sync_mark()
+
+    def _do_sync_mark(self) -> float:
+        torch.cuda.synchronize()
+        if self.tp:
+            self.tp.dist.barrier(group=self.tp.cpu)
+        t = time.perf_counter()
+        self._marks = getattr(self, "_marks", []) + [t]
+        return t
+
+    def max_elapsed(self) -> float:
+        """max over ranks of the time between the last two sync marks (seconds)."""
+        if self.tp and self.tp.rank == 0:
+            self.tp.bcast_step([_KIND_MAXELAPSED], None)
+        return self._do_max_elapsed()
+
+    def _do_max_elapsed(self) -> float:
+        e = torch.tensor([self._marks[-1] - self._marks[-2]], dtype=torch.float64)
+        if self.tp:
+            self.tp.dist.all_reduce(e, op=self.tp.dist.ReduceOp.MAX, group=self.tp.cpu)
+        return float(e[0])
+
     # ------------------------------------------------------------------ offline API
     def generate(self, prompts: Sequence[Sequence[int]], params: SamplingParams | Sequence[SamplingParams]) -> List[List[int]]:
         """Run the given token-id prompts to completion (continuous batching); returns output ids."""
@@ -203,6 +230,12 @@ class TPWorker:
             kind = h[0]
             if kind == _KIND_STOP:
                 return
+            if kind == _KIND_SYNC:
+                self.engine._do_sync_mark()
+                continue
+            if kind == _KIND_MAXELAPSED:
+                self.engine._do_max_elapsed()
+                continue
             if kind == _KIND_DECODE:
                 B = h[1]
                 run.decode(B, p[:B], p[B:2 * B], p[2 * B:].reshape(B, mb))

@@ -16,6 +16,26 @@ from .lib import B200Error, check, load
 BLOCK_SIZE = 16  # tokens per KV page (vLLM default block_size)
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the GEMM kernel (bench.py's live roofline).
+    Events are recorded on the launching stream around each launch; nothing is recorded while a
+    CUDA graph is being captured."""
+
+    def __init__(self):
+        self.records = []   # (tag, flops, bytes, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, flops, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(tag, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1; a["ms"] += e0.elapsed_time(e1); a["flops"] += flops; a["bytes"] += nbytes
+        return agg
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -134,8 +154,17 @@ def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1):
         shape = (splits, M, N) if splits > 1 else (M, N)
         out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     ldy = out.stride(-2)
+    timed = TIMER is not None and not torch.cuda.is_current_stream_capturing()
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(load().b200_gemm_bf16(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), ldy, out_f32,
                                 splits, _stream()), "gemm")
+    if timed:
+        e1.record()
+        tag = "gemm_prefill" if M > 256 else "gemm_decode"
+        TIMER.records.append((tag, 2.0 * M * N * K, 2.0 * (N * K + M * K) + (4.0 if out_f32 else 2.0) * M * N * splits,
+                              e0, e1))
     return out
 
 

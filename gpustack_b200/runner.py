@@ -62,7 +62,9 @@ class ModelRunner:
         self.num_blocks = 0
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.graph_pool = None
-        self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0}
+        self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0,
+                      "h2d_bytes": 0, "d2h_bytes": 0, "decode_kv_tokens": 0, "prefill_tokens": 0}
+        self.launches_per_decode = 0
 
     # ------------------------------------------------------------------------------ memory
     def _alloc_workspace(self):
@@ -154,6 +156,7 @@ class ModelRunner:
         m, w = self.mcfg, self.w
         pos, slots = self._pos, self._slots
         ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
+        self.stats["kernel_launches"] += 2   # embedding (by the caller) + this norm
         for l, lw in enumerate(w.layers):
             ops.gemm(self.xn[:T], lw.qkv, out=self.qkv[:T])
             if lw.qkv_bias is not None:
@@ -204,6 +207,8 @@ class ModelRunner:
             ops.paged_attn_decode(self.qkv[:B], self.qkv_width, self.k_cache[l], self.v_cache[l], bt, lens,
                                   self.attn_out[:B], self.Hq, self.Hkv, self.D, self.scale,
                                   num_splits=splits, workspace=ws)
+            if splits > 1:
+                self.stats["kernel_launches"] += 1   # split merge kernel
 
         self._layers(B, attn)
         self._sample(B, None)
@@ -216,7 +221,9 @@ class ModelRunner:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for B in sorted(self.ecfg.graph_buckets(), reverse=True):
+                k0 = self.stats["kernel_launches"]
                 self._decode_forward(B)          # warm-up (allocates workspaces, sets func attrs)
+                self.launches_per_decode = self.stats["kernel_launches"] - k0
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=self.graph_pool, stream=s):
@@ -227,6 +234,7 @@ class ModelRunner:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._buckets = sorted(self.graphs)
+        self.stats["kernel_launches"] = 0
 
     def decode(self, B: int, last_token: np.ndarray, num_computed: np.ndarray, block_table: np.ndarray) -> np.ndarray:
         """One decode step for rows 0..B-1 of the scheduler's persistent batch."""
@@ -253,11 +261,15 @@ class ModelRunner:
         if self.graphs:
             self.graphs[Bp].replay()
             self.stats["graph_replays"] += 1
+            self.stats["kernel_launches"] += self.launches_per_decode
         else:
             self._decode_forward(Bp)
         self.out_host[:B].copy_(self.out_ids[:B], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.stats["decode_steps"] += 1
+        self.stats["h2d_bytes"] += n * 4
+        self.stats["d2h_bytes"] += B * 4
+        self.stats["decode_kv_tokens"] += int(pos.sum()) + B
         return self.out_host[:B].numpy()
 
     # ------------------------------------------------------------------------------ prefill
@@ -317,6 +329,9 @@ class ModelRunner:
 
         self._layers(T, attn)
         self.stats["prefill_steps"] += 1
+        self.stats["h2d_bytes"] += end * 4
+        self.stats["d2h_bytes"] += ns * 4
+        self.stats["prefill_tokens"] += T
         if ns == 0:
             torch.cuda.current_stream().synchronize()
             return np.zeros(0, dtype=np.int32)

@@ -177,9 +177,13 @@ class OracleLlama:
     ($VLLM/model_executor/models/llama.py:316-333, 395-434) with a plain contiguous KV history per
     sequence.  bf16 tensors between operators, fp32 inside them."""
 
-    def __init__(self, cfg: LlamaConfig, weights: Dict[str, torch.Tensor]):
+    def __init__(self, cfg: LlamaConfig, weights: Dict[str, torch.Tensor], fp32_cache: bool = False):
+        """fp32_cache=True keeps an fp32 copy of every matmul weight (same arithmetic, no per-call
+        upcast) -- used when this oracle is timed as the CPU baseline."""
         self.cfg = cfg
         self.w = {k: v.to("cpu") for k, v in weights.items()}
+        self.wf = {k: v.to(torch.float32) for k, v in self.w.items() if v.dim() == 2 and "embed" not in k} \
+            if fp32_cache else {}
         self.cache = cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta)
         self.lm_head = self.w.get("lm_head.weight", self.w["model.embed_tokens.weight"])
         self.kv: Dict[int, List] = {}
@@ -187,8 +191,9 @@ class OracleLlama:
     def reset(self):
         self.kv = {}
 
-    def forward(self, seq_id: int, tokens: Sequence[int]) -> torch.Tensor:
-        """Append `tokens` to sequence `seq_id`; returns fp32 logits [len(tokens), vocab]."""
+    def forward(self, seq_id: int, tokens: Sequence[int], last_only: bool = False) -> torch.Tensor:
+        """Append `tokens` to sequence `seq_id`; returns fp32 logits [len(tokens), vocab]
+        (only the last position when last_only)."""
         cfg, w = self.cfg, self.w
         hist = self.kv.setdefault(seq_id, [None] * cfg.num_hidden_layers)
         start = 0 if hist[0] is None else hist[0][0].shape[0]
@@ -203,32 +208,41 @@ class OracleLlama:
                 res, x = h, rms_norm(h, w[p + "input_layernorm.weight"], cfg.rms_norm_eps)
             else:
                 x, res = fused_add_rms_norm(h, res, w[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-            q = linear(x, w[p + "self_attn.q_proj.weight"]).view(T, cfg.num_attention_heads, cfg.head_dim)
-            k = linear(x, w[p + "self_attn.k_proj.weight"]).view(T, cfg.num_key_value_heads, cfg.head_dim)
-            v = linear(x, w[p + "self_attn.v_proj.weight"]).view(T, cfg.num_key_value_heads, cfg.head_dim)
+            q = self._lin(x, p + "self_attn.q_proj.weight").view(T, cfg.num_attention_heads, cfg.head_dim)
+            k = self._lin(x, p + "self_attn.k_proj.weight").view(T, cfg.num_key_value_heads, cfg.head_dim)
+            v = self._lin(x, p + "self_attn.v_proj.weight").view(T, cfg.num_key_value_heads, cfg.head_dim)
             q, k = rope_neox(q, pos, self.cache), rope_neox(k, pos, self.cache)
             if hist[l] is None:
                 hist[l] = (k, v)
             else:
                 hist[l] = (torch.cat((hist[l][0], k)), torch.cat((hist[l][1], v)))
             a = attention_ref(q, hist[l][0], hist[l][1], scale, pos).reshape(T, cfg.q_size)
-            h = linear(a, w[p + "self_attn.o_proj.weight"])
+            h = self._lin(a, p + "self_attn.o_proj.weight")
             x, res = fused_add_rms_norm(h, res, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-            gu = torch.cat((linear(x, w[p + "mlp.gate_proj.weight"]), linear(x, w[p + "mlp.up_proj.weight"])), dim=-1)
-            h = linear(silu_and_mul(gu), w[p + "mlp.down_proj.weight"])
+            gu = torch.cat((self._lin(x, p + "mlp.gate_proj.weight"), self._lin(x, p + "mlp.up_proj.weight")), dim=-1)
+            h = self._lin(silu_and_mul(gu), p + "mlp.down_proj.weight")
         x, _ = fused_add_rms_norm(h, res, w["model.norm.weight"], cfg.rms_norm_eps)
-        return x.to(torch.float32) @ self.lm_head.to(torch.float32).t()
+        if last_only:
+            x = x[-1:]
+        lm = self.wf.get("lm_head.weight")
+        return x.to(torch.float32) @ (lm if lm is not None else self.lm_head.to(torch.float32)).t()
+
+    def _lin(self, x: torch.Tensor, name: str) -> torch.Tensor:
+        wf = self.wf.get(name)
+        if wf is None:
+            return linear(x, self.w[name])
+        return (x.to(torch.float32) @ wf.t()).to(x.dtype)
 
     def generate(self, seq_id: int, prompt: Sequence[int], max_new_tokens: int) -> List[int]:
         """greedy decode ($VLLM/v1/sample/sampler.py: argmax over fp32 logits, lowest index wins)."""
         out: List[int] = []
-        logits = self.forward(seq_id, prompt)[-1]
+        logits = self.forward(seq_id, prompt, last_only=True)[-1]
         for _ in range(max_new_tokens):
             nxt = int(torch.argmax(logits))
             out.append(nxt)
             if len(out) == max_new_tokens:
                 break
-            logits = self.forward(seq_id, [nxt])[-1]
+            logits = self.forward(seq_id, [nxt], last_only=True)[-1]
         return out
 
 
