@@ -258,6 +258,17 @@ static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int 
 
 using namespace b200;
 
+// Activation-tile width (tokens per MMA N): the smallest supported width that covers M, so a decode
+// batch is one tile column and no tensor-core work is spent on padding.
+extern "C" int b200_gemm_pick_block_x(int M, int N, int K) {
+  (void)N; (void)K;
+  if (M <= 16) return 16;
+  if (M <= 32) return 32;
+  if (M <= 64) return 64;
+  if (M <= 128) return 128;
+  return 256;
+}
+
 extern "C" int b200_gemm_suggest_splits(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0 || K % kBlockK) return 1;
   if (M > 256) return 1;  // prefill: tensor-bound, plenty of tiles
@@ -272,9 +283,9 @@ extern "C" int b200_gemm_suggest_splits(int M, int N, int K) {
   return splits;
 }
 
-extern "C" int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K,
-                              int64_t ldx, int64_t ldw, int64_t ldy, int out_f32, int splits,
-                              void* stream) {
+extern "C" int b200_gemm_bf16_ex(const void* X, const void* W, void* Y, int M, int N, int K,
+                                 int64_t ldx, int64_t ldw, int64_t ldy, int out_f32, int splits,
+                                 int block_x, void* stream) {
   B200_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(K % kBlockK == 0, "gemm: K=%d must be a multiple of %d", K, kBlockK);
   B200_REQUIRE(splits >= 1 && (K / kBlockK) % splits == 0,
@@ -289,9 +300,21 @@ extern "C" int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int 
     return B200_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (M <= 16) return launch_gemm<16>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
-  if (M <= 32) return launch_gemm<32>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
-  if (M <= 64) return launch_gemm<64>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
-  if (M <= 128) return launch_gemm<128>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
-  return launch_gemm<256>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+  if (block_x == 0) block_x = b200_gemm_pick_block_x(M, N, K);
+  switch (block_x) {
+    case 16: return launch_gemm<16>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+    case 32: return launch_gemm<32>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+    case 64: return launch_gemm<64>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+    case 128: return launch_gemm<128>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+    case 256: return launch_gemm<256>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
+    default:
+      b200_set_error("gemm: block_x=%d unsupported (16,32,64,128,256)", block_x);
+      return B200_ERR_INVALID;
+  }
+}
+
+extern "C" int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K,
+                              int64_t ldx, int64_t ldw, int64_t ldy, int out_f32, int splits,
+                              void* stream) {
+  return b200_gemm_bf16_ex(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, 0, stream);
 }

@@ -141,7 +141,7 @@ def gemm_suggest_splits(M: int, N: int, K: int) -> int:
     return load().b200_gemm_suggest_splits(M, N, K)
 
 
-def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1):
+def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1, block_x: int = 0):
     """y = x @ w.T (x [M,K], w [N,K], bf16).  splits>1 returns fp32 partials [splits, M, N]."""
     if not (x.is_cuda and w.is_cuda) or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise B200Error("gemm: bf16 CUDA tensors required")
@@ -158,8 +158,8 @@ def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1):
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(load().b200_gemm_bf16(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), ldy, out_f32,
-                                splits, _stream()), "gemm")
+    check(load().b200_gemm_bf16_ex(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), ldy, out_f32,
+                                   splits, block_x, _stream()), "gemm")
     if timed:
         e1.record()
         tag = "gemm_prefill" if M > 256 else "gemm_decode"

@@ -144,23 +144,28 @@ def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_l
             return {"id": rid, "object": o, "created": int(time.time()), "model": served_model_name, "choices": [ch]}
 
         async def events():
+            """yields (text_delta, finish_reason, is_first, n_out).  With stop strings the last
+            len(longest stop)-1 characters are held back until they can no longer start a match."""
             detok = IncrementalDetokenizer(tokenizer)
-            n_out, first, text_all, stopped = 0, True, "", False
+            n_out, first, pending = 0, True, ""
+            hold = max((len(s) for s in stops), default=1) - 1
             gen = aeng.generate(rid, prompt_ids, sp)
             try:
                 async for toks, fin in gen:
                     n_out += len(toks)
                     delta = detok.push(toks, final=fin is not None)
                     if stops:
-                        text_all += delta
-                        cut = min((text_all.find(s) for s in stops if s in text_all), default=-1)
+                        pending += delta
+                        cut = min((pending.find(s) for s in stops if s in pending), default=-1)
                         if cut >= 0:
-                            delta = delta[: max(0, len(delta) - (len(text_all) - cut))]
-                            fin, stopped = "stop", True
+                            yield pending[:cut], "stop", first, n_out
+                            return
+                        if fin is None and hold > 0:
+                            delta, pending = pending[:-hold] if len(pending) > hold else "", pending[-hold:]
+                        else:
+                            delta, pending = pending, ""
                     yield delta, fin, first, n_out
                     first = False
-                    if stopped:
-                        break
             finally:
                 await gen.aclose()
 

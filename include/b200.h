@@ -86,6 +86,11 @@ int b200_gather_rows(const void* x, const int32_t* rows, void* out, int n, int H
  * K % 64 == 0 required.  M, N arbitrary (tails are zero-filled by TMA and masked on store). */
 int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
                    int64_t ldw, int64_t ldy, int out_f32, int splits, void* stream);
+/* Same with an explicit activation-tile width block_x in {16,32,64,128,256} (0 = pick from M, see
+ * b200_gemm_pick_block_x); used by the tuning sweep in tools/gemm_sweep.py. */
+int b200_gemm_bf16_ex(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                      int64_t ldw, int64_t ldy, int out_f32, int splits, int block_x, void* stream);
+int b200_gemm_pick_block_x(int M, int N, int K);
 /* Y[m,n] = bf16(sum_s partials[s][m][n]). */
 int b200_splitk_reduce(const float* partials, int splits, void* Y, int M, int N, int64_t ldy,
                        void* stream);
@@ -109,6 +114,9 @@ int b200_paged_attn_decode(const void* q, int64_t q_stride, const void* k_cache,
  * the cache) and attends causally to cache positions [0, ctx_lens[s] + i].  K/V of the chunk must
  * already be in the cache (b200_rope_kv_write runs first).  tile_seq/tile_q0 [num_tiles] list the
  * (sequence, first query offset) of each 32-token query tile, built on the host. */
+/* query-tile size (tokens) the prefill kernel uses for this head grouping: 32 (group <= 4),
+ * 16 (group <= 8), 0 = unsupported. */
+int b200_attn_prefill_tile(int Hq, int Hkv);
 int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache,
                             const void* v_cache, const int32_t* block_table, int max_blocks,
                             const int32_t* cu_q, const int32_t* ctx_lens, const int32_t* tile_seq,
@@ -120,11 +128,14 @@ int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache
 int b200_ipc_get_handle(void* dev_ptr, void* handle_out_host /* 64 bytes */);
 int b200_ipc_open_handle(const void* handle_host /* 64 bytes */, void** dev_ptr_out);
 int b200_ipc_close_handle(void* dev_ptr);
-/* One-shot all-reduce(sum) of bf16 [n] fused with residual add + RMSNorm of the reduced rows:
- * peers[r] = rank r's staging buffer (bf16 [n], already filled by that rank's GEMM);
- * flags[r] = rank r's flag words (peer-mapped, >= 2*world uint32, zero-initialised once).
- * Every rank reduces all rows (redundantly) so no second exchange is needed.
- * w == NULL: plain all-reduce into y.  epoch must increase by 1 on every call. */
+/* uint32 words each rank's flag buffer must hold (zero-initialised once, peer-mapped). */
+int b200_allreduce_flag_words(int world);
+/* One-shot all-reduce(sum) of bf16 [T,H] fused with residual add + RMSNorm of the reduced rows:
+ * peers[r] = rank r's staging buffer (already filled by that rank's row-parallel GEMM);
+ * flags[r] = rank r's flag words.  Every rank reduces all rows (redundantly, in rank order, so
+ * results are bit-identical across ranks) -- no second exchange.  w == NULL: plain all-reduce
+ * into y.  Arrival epochs live on the device (CUDA-graph replays stay valid); `epoch` is unused.
+ * The caller alternates between two staging buffers on consecutive calls. */
 int b200_allreduce_add_rms_norm(void* const* peers_host, void* const* flags_host, int world,
                                 int rank, uint32_t epoch, const void* residual, const void* w,
                                 void* y, void* residual_out, int T, int H, float eps, void* stream);

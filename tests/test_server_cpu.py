@@ -1,0 +1,153 @@
+"""HTTP surface conformance without a GPU: a stub engine core produces tokens; every streamed
+chunk must validate as openai.types.chat.ChatCompletionChunk exactly as GPUStack's
+ModelUsageMiddleware parses them (gpustack/api/middlewares.py:241-250 in the reference), usage must
+arrive in the final chunk, and the plumbing endpoints must satisfy GPUStack's probes."""
+import json
+import time
+
+import numpy as np
+import pytest
+from fastapi.testclient import TestClient
+from openai.types.chat import ChatCompletion, ChatCompletionChunk
+from openai.types.completion import Completion
+
+from gpustack_b200.async_engine import AsyncEngine
+from gpustack_b200.scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler
+from gpustack_b200.server import create_app
+from gpustack_b200.tokenizer import ByteTokenizer
+
+
+class StubEngine:
+    """Scheduler-accurate engine core whose 'GPU' emits the bytes of a fixed sentence."""
+
+    TEXT = "Hello from the stub engine. "
+
+    def __init__(self):
+        self.sched = Scheduler(256, 16, 8, 128, 512, eos_token_id=2)
+        self.requests, self.counters = {}, {"generation_tokens": 0}
+        self.tok = ByteTokenizer(600)
+        self.ids = self.tok.encode(self.TEXT * 20, add_bos=False)
+
+    def add_request(self, rid, prompt_ids, params):
+        r = Request(rid, list(prompt_ids), params)
+        self.sched.add(r)
+        self.requests[rid] = r
+
+    def abort_request(self, rid):
+        self.sched.abort(rid)
+
+    def has_work(self):
+        return self.sched.has_work()
+
+    def _next(self, r):
+        return self.ids[len(r.output_ids) % len(self.ids)]
+
+    def step(self):
+        plan = self.sched.schedule()
+        if plan is None:
+            return None
+        time.sleep(0.001)
+        if isinstance(plan, PrefillPlan):
+            out = self.sched.update_prefill(plan, [self._next(r) for r, s in zip(plan.reqs, plan.sample) if s])
+        else:
+            toks = np.array([self._next(r) for r in self.sched.rows], dtype=np.int32)
+            out = self.sched.update_decode(plan, toks)
+        self.counters["generation_tokens"] += len(out.token_ids)
+        return out
+
+    def shutdown(self):
+        pass
+
+
+@pytest.fixture(scope="module")
+def client():
+    eng = StubEngine()
+    aeng = AsyncEngine(eng)
+    app = create_app(aeng, eng.tok, "stub-model", 512)
+    with TestClient(app) as c:
+        yield c
+    aeng._stop = True
+
+
+def _sse(resp):
+    events = []
+    for line in resp.iter_lines():
+        if line.startswith("data: "):
+            events.append(line[6:])
+    return events
+
+
+def test_plumbing_endpoints(client):
+    assert client.get("/health").status_code == 200
+    assert client.get("/version").json()["version"]
+    m = client.get("/v1/models").json()
+    assert m["data"][0]["id"] == "stub-model" and m["data"][0]["max_model_len"] == 512
+    text = client.get("/metrics").text
+    for name in ("vllm:num_requests_running", "vllm:num_requests_waiting", "vllm:kv_cache_usage_perc",
+                 "vllm:prompt_tokens_total", "vllm:generation_tokens_total", "vllm:request_success_total",
+                 "vllm:time_to_first_token_seconds_bucket", "vllm:time_per_output_token_seconds_bucket",
+                 "vllm:e2e_request_latency_seconds_count"):
+        assert name in text, name
+
+
+def test_chat_stream_chunks_validate_like_gpustack_parses_them(client):
+    body = {"model": "stub-model", "messages": [{"role": "user", "content": "hi"}], "max_completion_tokens": 24,
+            "stream": True, "stream_options": {"include_usage": True}, "ignore_eos": True}
+    with client.stream("POST", "/v1/chat/completions", json=body) as resp:
+        assert resp.status_code == 200 and resp.headers["content-type"].startswith("text/event-stream")
+        events = _sse(resp)
+    assert events[-1] == "[DONE]"
+    chunks = [ChatCompletionChunk.model_validate(json.loads(e)) for e in events[:-1]]
+    assert chunks[0].choices[0].delta.role == "assistant"
+    text = "".join(c.choices[0].delta.content or "" for c in chunks if c.choices)
+    assert text == (StubEngine.TEXT * 20)[:24]
+    finals = [c for c in chunks if c.choices and c.choices[0].finish_reason]
+    assert len(finals) == 1 and finals[0].choices[0].finish_reason == "length"
+    usage = chunks[-1].usage
+    assert chunks[-1].choices == [] and usage.completion_tokens == 24
+    assert usage.total_tokens == usage.prompt_tokens + 24
+
+
+def test_non_stream_chat_and_completions(client):
+    r = client.post("/v1/chat/completions", json={"model": "stub-model", "max_tokens": 10, "ignore_eos": True,
+                                                  "messages": [{"role": "user", "content": "x"}]})
+    c = ChatCompletion.model_validate(r.json())
+    assert c.choices[0].message.content == StubEngine.TEXT[:10] and c.usage.completion_tokens == 10
+    r = client.post("/v1/completions", json={"model": "stub-model", "prompt": [5, 6, 7, 8], "max_tokens": 7,
+                                             "ignore_eos": True})
+    c = Completion.model_validate(r.json())
+    assert c.usage.prompt_tokens == 4 and c.choices[0].text == StubEngine.TEXT[:7]
+    assert c.choices[0].finish_reason == "length"
+
+
+def test_stop_string_truncates_and_reports_stop(client):
+    r = client.post("/v1/completions", json={"model": "stub-model", "prompt": "abc", "max_tokens": 60,
+                                             "ignore_eos": True, "stop": ["stub"]})
+    j = r.json()
+    assert j["choices"][0]["text"] == "Hello from the " and j["choices"][0]["finish_reason"] == "stop"
+
+
+def test_error_envelopes(client):
+    r = client.post("/v1/chat/completions", json={"model": "other", "messages": [{"role": "user", "content": "x"}]})
+    assert r.status_code == 404 and r.json()["error"]["code"] == "model_not_found"
+    r = client.post("/v1/completions", json={"model": "stub-model", "prompt": "x" * 600, "max_tokens": 5})
+    assert r.status_code == 400 and "maximum context length" in r.json()["error"]["message"]
+    r = client.post("/v1/chat/completions", json={"model": "stub-model", "messages": []})
+    assert r.status_code == 400 and r.json()["error"]["type"] == "invalid_request_error"
+    r = client.post("/v1/completions", content=b"{not json", headers={"content-type": "application/json"})
+    assert r.status_code == 400
+
+
+def test_many_concurrent_streams(client):
+    import concurrent.futures as cf
+
+    def one(i):
+        with client.stream("POST", "/v1/completions", json={"model": "stub-model", "prompt": [3 + i, 9], "max_tokens": 16,
+                                                            "stream": True, "ignore_eos": True,
+                                                            "stream_options": {"include_usage": True}}) as resp:
+            ev = _sse(resp)
+        u = json.loads(ev[-2])["usage"]
+        return u["completion_tokens"]
+
+    with cf.ThreadPoolExecutor(16) as ex:
+        assert list(ex.map(one, range(32))) == [16] * 32
