@@ -258,27 +258,45 @@ static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int 
 
 using namespace b200;
 
-// Activation-tile width (tokens per MMA N): the smallest supported width that covers M, so a decode
-// batch is one tile column and no tensor-core work is spent on padding.
-extern "C" int b200_gemm_pick_block_x(int M, int N, int K) {
-  (void)N; (void)K;
-  if (M <= 16) return 16;
-  if (M <= 32) return 32;
-  if (M <= 64) return 64;
-  if (M <= 128) return 128;
-  return 256;
+// ---- decode-shape planning (M <= 256), from the sweep in tools/gemm_sweep.py ------------------
+// A tile's cost is dominated by the bytes its SM has to ingest (weight tile + activation tile, the
+// latter from L2), so the plan spreads one GEMM over ~one wave of CTAs (units = n_tiles * m_tiles
+// * splits close to the SM count) and prefers splitting K (no re-read) over splitting M (weights
+// re-read from L2) when K is long.
+static int pow2_cover(int M) {
+  int b = 16;
+  while (b < M && b < 256) b <<= 1;
+  return b;
 }
 
+// Activation-tile width for a given split count.
+static int plan_block_x(int M, int N, int splits) {
+  if (M > 256) return 256;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int base = pow2_cover(M);
+  const int units = ((N + kBlockW - 1) / kBlockW) * splits;
+  if (base >= 64 && units * 2 <= sms + sms / 12) return base / 2;  // two m-tiles fill the wave
+  return base;
+}
+
+extern "C" int b200_gemm_pick_block_x(int M, int N, int K) {
+  (void)K;
+  return plan_block_x(M, N, 1);
+}
+
+// K-splits for the row-parallel projections (O, down), whose fp32 partials are consumed for free
+// by b200_fused_add_rms_norm_partials.
 extern "C" int b200_gemm_suggest_splits(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0 || K % kBlockK) return 1;
   if (M > 256) return 1;  // prefill: tensor-bound, plenty of tiles
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int kb = K / kBlockK;
+  int f = sms / n_tiles;             // how many units per weight tile one wave can hold
+  if (f < 2) return 1;
+  if (K < 8192 && M > 32) f /= 2;    // short K: let two m-tiles take half of the factor
   int splits = 1;
-  // HBM-bound decode: want >= ~1 CTA per SM streaming weights, but keep >= 8 k-blocks per split
-  while (n_tiles * splits * 2 <= sms && splits < 8 && kb % (splits * 2) == 0 &&
-         kb / (splits * 2) >= 8)
+  while (splits * 2 <= f && splits < 8 && kb % (splits * 2) == 0 && kb / (splits * 2) >= 8)
     splits *= 2;
   return splits;
 }
@@ -300,7 +318,7 @@ extern "C" int b200_gemm_bf16_ex(const void* X, const void* W, void* Y, int M, i
     return B200_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (block_x == 0) block_x = b200_gemm_pick_block_x(M, N, K);
+  if (block_x == 0) block_x = plan_block_x(M, N, splits);
   switch (block_x) {
     case 16: return launch_gemm<16>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);
     case 32: return launch_gemm<32>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, s);

@@ -1,0 +1,30 @@
+"""Tensor-parallel engine parity (needs >= 2 GPUs; skipped otherwise)."""
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("eager", ["1", "0"])
+def test_tp_engine_matches_oracle(world, eager):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER=eager))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout

@@ -1,0 +1,84 @@
+"""World-size-2 gloo test (CPU) of the tensor-parallel step protocol: rank 0's scheduler output
+must reach rank 1's runner unchanged for decode and (chunked) prefill steps, and the sync/timing
+helpers must not deadlock."""
+import multiprocessing as mp
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class FakeRunner:
+    max_blocks = 6
+
+    def __init__(self):
+        self.calls = []
+
+    def decode(self, B, last, computed, table):
+        self.calls.append(("decode", int(B), np.asarray(last[:B]).tolist(), np.asarray(computed[:B]).tolist(),
+                           np.asarray(table[:B]).tolist()))
+        return np.arange(B, dtype=np.int32)
+
+    def prefill(self, chunks, starts, tables, sample):
+        self.calls.append(("prefill", [list(map(int, c)) for c in chunks], list(map(int, starts)),
+                           [list(map(int, t)) for t in tables], [bool(s) for s in sample]))
+        return np.zeros(sum(bool(s) for s in sample), dtype=np.int32)
+
+
+def _worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
+    import torch
+    import torch.distributed as dist
+
+    from gpustack_b200 import engine as E
+
+    dist.init_process_group(backend="gloo", rank=rank, world_size=2)
+    tp = E.TPContext(rank, 2, torch.device("cpu"))
+    eng = E.LLMEngine.__new__(E.LLMEngine)      # protocol only: no GPU objects
+    eng.tp, eng.runner = tp, FakeRunner()
+    torch.cuda.synchronize = lambda *a, **k: None
+    steps = [
+        ("decode", 3, [7, 8, 9], [20, 33, 5], [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]]),
+        ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False]),
+    ]
+    if rank == 0:
+        for s in steps:
+            if s[0] == "decode":
+                _, B, last, comp, tab = s
+                payload = np.concatenate([np.array(last), np.array(comp), np.array(tab).reshape(-1)]).astype(np.int32)
+                tp.bcast_step([E._KIND_DECODE, B], payload)
+            else:
+                eng._bcast_prefill(s[1], s[2], s[3], s[4])
+        eng.sync_mark(); eng.sync_mark()
+        dt = eng.max_elapsed()
+        eng.shutdown()
+        q.put(("rank0", dt >= 0.0))
+    else:
+        E.TPWorker(eng).serve_forever()
+        q.put(("rank1", eng.runner.calls))
+    dist.destroy_process_group()
+
+
+def test_step_broadcast_roundtrip():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _port()
+    ps = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got["rank0"] is True
+    calls = got["rank1"]
+    assert calls[0] == ("decode", 3, [7, 8, 9], [20, 33, 5],
+                        [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]])
+    assert calls[1] == ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False])

@@ -1,0 +1,67 @@
+"""Tensor-parallel parity check, launched with torch.distributed.run (one rank per GPU) by
+tests/test_tp_gpu.py:  the TP engine must reproduce the CPU oracle's logits (stated tolerance
+2e-2 * max|logit|) and the single-GPU engine's greedy tokens."""
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+
+from gpustack_b200.config import EngineConfig, ModelConfig
+from gpustack_b200.engine import LLMEngine, TPWorker
+from gpustack_b200.scheduler import SamplingParams
+from oracle import llama_oracle as O
+
+
+def main():
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    c = O.LlamaConfig(vocab_size=1000, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=8, num_key_value_heads=world if world <= 8 else 8, head_dim=64,
+                      max_position_embeddings=512)
+    if c.num_attention_heads % c.num_key_value_heads:
+        c.num_attention_heads = c.num_key_value_heads * 2
+    mcfg = ModelConfig(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                       num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                       num_key_value_heads=c.num_key_value_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
+                       max_position_embeddings=c.max_position_embeddings, eos_token_id=2)
+    weights = O.init_weights(c, seed=21)
+    ecfg = EngineConfig(tensor_parallel_size=world, max_num_seqs=8, max_num_batched_tokens=128, num_gpu_blocks=128,
+                        cuda_graph_sizes=[1, 2, 4, 8], enforce_eager=os.environ.get("TP_EAGER", "0") == "1")
+    eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
+    if rank != 0:
+        TPWorker(eng).serve_forever()
+        return
+    g = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(3, c.vocab_size, (n,), generator=g).tolist() for n in (9, 40, 77, 130)]
+    oracle = O.OracleLlama(c, weights)
+    res = {"world": world, "ok": True, "checks": []}
+    outs = eng.generate(prompts, SamplingParams(max_tokens=12, ignore_eos=True))
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        oracle.reset()
+        logits = oracle.forward(i, p)[-1]
+        n_ok = n_chk = 0
+        for t in range(len(o)):
+            top2 = torch.topk(logits, 2).values
+            if float(top2[0] - top2[1]) > 2e-2 * float(logits.abs().max()):
+                n_chk += 1
+                n_ok += int(int(torch.argmax(logits)) == o[t])
+            logits = oracle.forward(i, [o[t]])[-1]
+        res["checks"].append({"seq": i, "checked": n_chk, "agree": n_ok})
+        if n_ok != n_chk or n_chk < 3:
+            res["ok"] = False
+    eng.shutdown()
+    print("TP_PARITY " + json.dumps(res), flush=True)
+    if not res["ok"]:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.destroy_process_group()
