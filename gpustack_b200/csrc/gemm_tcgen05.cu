@@ -75,7 +75,13 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
   return c;
 }
 
-template <int BLOCK_X>
+// EPI 0: store the accumulator (bf16, or fp32 / split-K partials).
+// EPI 1: SiLU*mul epilogue for the gate_up projection ($VLLM activation.py:133-143 fused into the
+//        producing GEMM): W rows are interleaved (row 2i = gate_i, row 2i+1 = up_i), so the two
+//        values of an output channel sit in adjacent TMEM lanes = adjacent threads of one warp;
+//        a lane pair swaps halves with one shuffle per two tokens and writes
+//        act[m, i] = bf16(bf16(silu(bf16(g))) * bf16(u)) -- the same roundings as the unfused path.
+template <int BLOCK_X, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
@@ -193,7 +199,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
         if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, r);
         else tmem_ld_32x16(t_addr + c0, r);
         tmem_ld_wait();
-        if (n < N) {
+        if constexpr (EPI == 1) {
+          const int ch = n >> 1;          // output channel of this lane pair
+          bf16* dst = Yb + (size_t)(m_base + c0) * ldy + ch;
+          const bool odd = lane & 1;
+#pragma unroll
+          for (int j = 0; j < CH; j += 2) {
+            // even lane (gate row) computes token j, odd lane (up row) computes token j+1
+            const uint32_t send = odd ? r[j] : r[j + 1];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float g = round_bf16(__uint_as_float(odd ? recv : r[j]));
+            const float up = round_bf16(__uint_as_float(odd ? r[j + 1] : recv));
+            const float sg = round_bf16(g / (1.f + __expf(-g)));
+            const int m = m_base + c0 + j + (odd ? 1 : 0);
+            if (n < N && m < M) dst[(size_t)(j + (odd ? 1 : 0)) * ldy] = __float2bfloat16_rn(sg * up);
+          }
+        } else if (n < N) {
           if (out_f32) {
             float* dst = Yf + split_off + (size_t)(m_base + c0) * ldy + n;
 #pragma unroll
@@ -222,13 +243,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   }
 }
 
-template <int BLOCK_X>
+template <int BLOCK_X, int EPI = 0>
 static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
                        int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_X>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_X>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_X, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -249,7 +270,7 @@ static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int 
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
   const int group_m = m_tiles < 8 ? m_tiles : 8;
-  gemm_bf16_tcgen05_kernel<BLOCK_X><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
+  gemm_bf16_tcgen05_kernel<BLOCK_X, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
       tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
   return b200_check_launch("b200_gemm_bf16");
 }
@@ -328,6 +349,27 @@ extern "C" int b200_gemm_bf16_ex(const void* X, const void* W, void* Y, int M, i
     default:
       b200_set_error("gemm: block_x=%d unsupported (16,32,64,128,256)", block_x);
       return B200_ERR_INVALID;
+  }
+}
+
+extern "C" int b200_gemm_bf16_silu_mul(const void* X, const void* W, void* Y, int M, int N, int K,
+                                       int64_t ldx, int64_t ldw, int64_t ldy, void* stream) {
+  B200_REQUIRE(M >= 0 && N > 0 && K > 0 && N % 2 == 0, "gemm_silu_mul: bad shape M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(K % kBlockK == 0, "gemm_silu_mul: K=%d must be a multiple of %d", K, kBlockK);
+  B200_REQUIRE(ldx >= K && ldw >= K && ldy >= N / 2, "gemm_silu_mul: leading dimensions too small");
+  if (M == 0) return B200_OK;
+  const DeviceInfo& d = device_info();
+  if (!d.valid || d.cc_major != 10) {
+    b200_set_error("gemm: tcgen05 kernel needs an sm_100 device (found cc %d.%d)", d.cc_major, d.cc_minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (plan_block_x(M, N, 1)) {
+    case 16: return launch_gemm<16, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, s);
+    case 32: return launch_gemm<32, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, s);
+    case 64: return launch_gemm<64, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, s);
+    case 128: return launch_gemm<128, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, s);
+    default: return launch_gemm<256, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, s);
   }
 }
 

@@ -71,7 +71,7 @@ class LLMEngine:
         if ecfg.max_model_len is None:
             ecfg.max_model_len = mcfg.max_position_embeddings
         ecfg.max_model_len = min(ecfg.max_model_len, mcfg.max_position_embeddings)
-        self.runner = ModelRunner(mcfg, ecfg, weights, device=device, tp_group=tp.nccl if tp else None)
+        self.runner = ModelRunner(mcfg, ecfg, weights, device=device, tp_group=tp.nccl if tp else None, tp_ctx=tp)
         n = self.runner.profile_num_blocks()
         if tp:   # every rank must use the same block count
             t = torch.tensor([n], dtype=torch.int64)

@@ -168,6 +168,33 @@ def gemm(x, w, out=None, out_dtype=torch.bfloat16, splits: int = 1, block_x: int
     return out
 
 
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """[I,H] gate and up weights -> [2I,H] with row 2i = gate_i, row 2i+1 = up_i (the layout
+    gemm_silu_mul expects)."""
+    return torch.stack((gate, up), dim=1).reshape(2 * gate.shape[0], gate.shape[1]).contiguous()
+
+
+def gemm_silu_mul(x, w_interleaved, out=None):
+    """act = silu(x @ gate.T) * (x @ up.T) in one kernel; w_interleaved from interleave_gate_up."""
+    if not (x.is_cuda and w_interleaved.is_cuda) or x.dtype != torch.bfloat16 or w_interleaved.dtype != torch.bfloat16:
+        raise B200Error("gemm_silu_mul: bf16 CUDA tensors required")
+    M, K = x.shape
+    N = w_interleaved.shape[0]
+    if out is None:
+        out = torch.empty((M, N // 2), dtype=torch.bfloat16, device=x.device)
+    timed = TIMER is not None and not torch.cuda.is_current_stream_capturing()
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(load().b200_gemm_bf16_silu_mul(_p(x), _p(w_interleaved), _p(out), M, N, K, x.stride(0),
+                                         w_interleaved.stride(0), out.stride(0), _stream()), "gemm_silu_mul")
+    if timed:
+        e1.record()
+        TIMER.records.append(("gemm_prefill" if M > 256 else "gemm_decode", 2.0 * M * N * K,
+                              2.0 * (N * K + M * K) + 1.0 * M * N, e0, e1))
+    return out
+
+
 def splitk_reduce(partials, out=None):
     _req(partials, torch.float32, "partials")
     S, M, N = partials.shape

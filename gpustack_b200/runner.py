@@ -15,6 +15,7 @@ pinned int32 staging buffer copied host->device with a single cudaMemcpyAsync.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -35,7 +36,7 @@ def _align(n: int, a: int = 4) -> int:
 
 class ModelRunner:
     def __init__(self, mcfg: ModelConfig, ecfg: EngineConfig, weights: ModelWeights, device: str = "cuda",
-                 tp_group=None):
+                 tp_group=None, tp_ctx=None):
         if not torch.cuda.is_available():
             raise B200Error("ModelRunner needs a CUDA device: this engine has no CPU path")
         self.mcfg, self.ecfg, self.w = mcfg, ecfg, weights
@@ -62,6 +63,12 @@ class ModelRunner:
         self.num_blocks = 0
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.graph_pool = None
+        self.oneshot = None
+        self._ar_toggle = 0
+        if self.tp > 1 and tp_ctx is not None and os.environ.get("B200_TP_ALLREDUCE", "oneshot") == "oneshot":
+            from .tp_comm import OneShotAllReduce
+
+            self.oneshot = OneShotAllReduce(tp_ctx, min(512, self.max_tokens), self.H, self.device)
         self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0,
                       "h2d_bytes": 0, "d2h_bytes": 0, "decode_kv_tokens": 0, "prefill_tokens": 0}
         self.launches_per_decode = 0
@@ -75,7 +82,6 @@ class ModelRunner:
         self.xn = e(T, H)
         self.qkv = e(T, self.qkv_width)
         self.attn_out = e(T, self.Hq * self.D)
-        self.gu = e(T, 2 * self.I)
         self.act = e(T, self.I)
         self.x_last = e(self.max_seqs, H)
         self.logits = e(self.max_seqs, self.v_local, dt=torch.float32)
@@ -133,6 +139,16 @@ class ModelRunner:
         """O / down projection followed by (all-reduce +) residual add + RMSNorm -> self.xn."""
         eps = self.mcfg.rms_norm_eps
         if self.tp > 1:
+            ar = self.oneshot
+            if ar is not None and T <= ar.max_tokens:
+                # GEMM writes its partial into a peer-mapped staging buffer; ONE kernel then pulls
+                # every rank's partial over NVLink, sums, adds the residual and normalises.
+                which = self._ar_toggle
+                self._ar_toggle ^= 1
+                ops.gemm(x, w, out=ar.stage(which, T))
+                ar.allreduce_add_rms_norm(which, self.resid[:T], norm_w, self.xn[:T], self.resid[:T], T, eps)
+                self.stats["kernel_launches"] += 2
+                return
             ops.gemm(x, w, out=self.hbuf[:T])
             torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
             ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
@@ -165,11 +181,10 @@ class ModelRunner:
                               self.Hq, self.Hkv, self.D)
             attn_fn(l)
             self._row_parallel(self.attn_out[:T], lw.o, T, lw.post_norm)
-            ops.gemm(self.xn[:T], lw.gate_up, out=self.gu[:T])
-            ops.silu_and_mul(self.gu[:T], out=self.act[:T])
+            ops.gemm_silu_mul(self.xn[:T], lw.gate_up, out=self.act[:T])   # SiLU*mul in the epilogue
             nxt = w.layers[l + 1].input_norm if l + 1 < len(w.layers) else w.final_norm
             self._row_parallel(self.act[:T], lw.down, T, nxt)
-            self.stats["kernel_launches"] += 5
+            self.stats["kernel_launches"] += 4
 
     def _sample(self, n: int, rows: Optional[torch.Tensor]) -> None:
         """greedy token of n sequences into self.out_ids[:n]; rows = last-token row of each."""

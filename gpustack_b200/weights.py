@@ -26,7 +26,7 @@ class LayerWeights:
     qkv_bias: Optional[torch.Tensor]
     o: torch.Tensor               # [H, Hq/t * D]
     post_norm: torch.Tensor       # [H]
-    gate_up: torch.Tensor         # [2I/t, H]  (gate rows then up rows)
+    gate_up: torch.Tensor         # [2I/t, H]  rows interleaved: 2i = gate_i, 2i+1 = up_i (fused SiLU*mul epilogue)
     down: torch.Tensor            # [H, I/t]
 
 
@@ -78,7 +78,7 @@ def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank:
             qkv=dev(torch.cat([q, k, v], dim=0)), qkv_bias=bias,
             o=dev(get(p + "self_attn.o_proj.weight")[:, rank * hq * D:(rank + 1) * hq * D]),
             post_norm=dev(get(p + "post_attention_layernorm.weight")),
-            gate_up=dev(torch.cat([g, u], dim=0)),
+            gate_up=dev(torch.stack([g, u], dim=1).reshape(2 * I, -1)),
             down=dev(get(p + "mlp.down_proj.weight")[:, rank * I:(rank + 1) * I])))
     embed = dev(get("model.embed_tokens.weight"))
     V = cfg.vocab_size

@@ -91,6 +91,12 @@ int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int N, int K, i
 int b200_gemm_bf16_ex(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
                       int64_t ldw, int64_t ldy, int out_f32, int splits, int block_x, void* stream);
 int b200_gemm_pick_block_x(int M, int N, int K);
+/* gate_up projection with the SiLU*mul activation ($VLLM activation.py:133-143) fused into the
+ * epilogue.  W [N=2I, K] holds gate and up rows INTERLEAVED (row 2i = gate_i, row 2i+1 = up_i);
+ * Y [M, ldy >= I] bf16 = bf16(bf16(silu(bf16(g))) * bf16(u)): bit-identical to
+ * b200_gemm_bf16 followed by b200_silu_and_mul. */
+int b200_gemm_bf16_silu_mul(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                            int64_t ldw, int64_t ldy, void* stream);
 /* Y[m,n] = bf16(sum_s partials[s][m][n]). */
 int b200_splitk_reduce(const float* partials, int splits, void* Y, int M, int N, int64_t ldy,
                        void* stream);

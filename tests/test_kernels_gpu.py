@@ -182,6 +182,23 @@ def test_gemm(ops, M, N, K, splits, f32, out_dir):
         _close(y, ref, 1e-2 * scale, 1.6e-2, f"gemm {M}x{N}x{K}", out_dir)
 
 
+@pytest.mark.parametrize("M,I,K", [(1, 256, 128), (7, 1024, 512), (64, 14336, 4096), (200, 1792, 4096),
+                                   (256, 14336, 4096), (1000, 14336, 4096), (33, 104, 64)])
+def test_gemm_silu_mul_fused_equals_unfused(ops, M, I, K, out_dir):
+    """gate_up GEMM with the SiLU*mul epilogue is bit-identical to GEMM followed by silu_and_mul,
+    and within tolerance of the CPU oracle."""
+    g = torch.Generator(device="cuda").manual_seed(M + I)
+    x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+    wg = (torch.randn(I, K, generator=g, device="cuda") * 0.03).to(BF)
+    wu = (torch.randn(I, K, generator=g, device="cuda") * 0.03).to(BF)
+    fused = ops.gemm_silu_mul(x, ops.interleave_gate_up(wg, wu))
+    unfused = ops.silu_and_mul(ops.gemm(x, torch.cat([wg, wu], dim=0).contiguous()))
+    assert torch.equal(fused, unfused)
+    if M * I <= 64 * 14336:
+        ref = O.silu_and_mul(torch.cat([O.linear(x.cpu(), wg.cpu()), O.linear(x.cpu(), wu.cpu())], dim=-1))
+        _close(fused, ref, 2e-2, 3.2e-2, f"gemm_silu_mul {M}x{I}x{K}", out_dir)
+
+
 def test_gemm_vs_cpu_oracle(ops, out_dir):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(40, 512, generator=g).to(BF); w = (torch.randn(640, 512, generator=g) * 0.05).to(BF)

@@ -19,12 +19,13 @@ def _port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("allreduce", ["oneshot", "nccl"])
 @pytest.mark.parametrize("eager", ["1", "0"])
-def test_tp_engine_matches_oracle(world, eager):
+def test_tp_engine_matches_oracle(world, eager, allreduce):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER=eager))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER=eager, B200_TP_ALLREDUCE=allreduce))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout
