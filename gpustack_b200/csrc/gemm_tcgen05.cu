@@ -20,6 +20,8 @@
 #include "runtime.h"
 #include "../../include/b200.h"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int kBlockW = 128;  // weight rows per tile  (UMMA M)
@@ -81,7 +83,12 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
 //        values of an output channel sit in adjacent TMEM lanes = adjacent threads of one warp;
 //        a lane pair swaps halves with one shuffle per two tokens and writes
 //        act[m, i] = bf16(bf16(silu(bf16(g))) * bf16(u)) -- the same roundings as the unfused path.
-template <int BLOCK_X, int EPI>
+// MC 2: the kernel runs as clusters of two CTAs that own ADJACENT weight tiles of the same
+//       (m-tile, k-split).  Each CTA loads its own weight tile and HALF of the shared activation
+//       tile, multicast into both CTAs' shared memory, so the activation bytes an SM has to ingest
+//       from L2 are halved (the measured limiter of decode-shaped tiles).  Stage release is a
+//       multicast tcgen05.commit: a slot is reused only after BOTH CTAs' MMAs have read it.
+template <int BLOCK_X, int EPI, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
@@ -100,13 +107,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC);  // one multicast commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -120,11 +128,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kb_per_split = (K / kBlockK) / splits;
-  const int total_units = n_tiles * m_tiles * splits;
+  // with MC == 2 a "unit" is a PAIR of adjacent weight tiles; this CTA takes tile 2*pair + crank
+  const int n_units = (n_tiles + MC - 1) / MC;
+  const int total_units = n_units * m_tiles * splits;
+  const int first_unit = MC > 1 ? (int)(blockIdx.x / MC) : (int)blockIdx.x;
+  const int unit_stride = MC > 1 ? (int)(gridDim.x / MC) : (int)gridDim.x;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -132,17 +145,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
       const uint64_t hint_w = (m_tiles > 1) ? kEvictNormal : kEvictFirst;
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const TileCoord c = decode_unit(u, n_tiles, m_tiles, splits, group_m);
+      for (int u = first_unit; u < total_units; u += unit_stride) {
+        const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
+        const int n_tile = c.n_tile * MC + (int)crank;
         const int k0 = c.split * kb_per_split * kBlockK;
         for (int kb = 0; kb < kb_per_split; ++kb) {
           mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
           uint8_t* a = smem + stage * Cfg::kStageBytes;
           uint8_t* b = a + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(a, &tmap_w, &full_bar[stage], k0 + kb * kBlockK, c.n_tile * kBlockW, hint_w);
-          tma_load_2d(b, &tmap_x, &full_bar[stage], k0 + kb * kBlockK, c.m_tile * BLOCK_X,
-                      kEvictLast);
+          tma_load_2d(a, &tmap_w, &full_bar[stage], k0 + kb * kBlockK, n_tile * kBlockW, hint_w);
+          if constexpr (MC > 1) {
+            constexpr int HALF = BLOCK_X / MC;  // rows of the activation tile this CTA fetches
+            tma_load_2d_mc(b + crank * (HALF * kBlockK * 2), &tmap_x, &full_bar[stage],
+                           k0 + kb * kBlockK, c.m_tile * BLOCK_X + (int)crank * HALF,
+                           (uint16_t)((1u << MC) - 1), kEvictLast);
+          } else {
+            tma_load_2d(b, &tmap_x, &full_bar[stage], k0 + kb * kBlockK, c.m_tile * BLOCK_X,
+                        kEvictLast);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -155,7 +176,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = first_unit; u < total_units; u += unit_stride) {
         mbar_wait_guarded(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_X);
@@ -169,7 +190,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
             umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
                       umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in every CTA that multicasts into it) once these MMAs retire
+          if constexpr (MC > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << MC) - 1));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -183,11 +206,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
     uint32_t acc_phase = 0;
     bf16* Yb = reinterpret_cast<bf16*>(Yv);
     float* Yf = reinterpret_cast<float*>(Yv);
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const TileCoord c = decode_unit(u, n_tiles, m_tiles, splits, group_m);
+    for (int u = first_unit; u < total_units; u += unit_stride) {
+      const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
       mbar_wait_guarded(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int n = c.n_tile * kBlockW + quad * 32 + lane;
+      const int n = (c.n_tile * MC + (int)crank) * kBlockW + quad * 32 + lane;
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
       const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
@@ -237,42 +260,80 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while its peer may still write into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_X, int EPI = 0>
-static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
-                       int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
+static int g_gemm_multicast = -1;  // -1: read B200_GEMM_MULTICAST once (default on)
+
+static bool gemm_multicast_enabled() {
+  if (g_gemm_multicast < 0) {
+    const char* e = getenv("B200_GEMM_MULTICAST");
+    g_gemm_multicast = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_gemm_multicast != 0;
+}
+
+template <int BLOCK_X, int EPI, int MC>
+static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y, int M, int N, int K,
+                          int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_X>;
+  auto kernel = gemm_bf16_tcgen05_kernel<BLOCK_X, EPI, MC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_X, EPI>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
-      b200_set_error("gemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
-                     cudaGetErrorString(e));
+      b200_set_error("gemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return B200_ERR_CUDA;
     }
     attr_set = true;
   }
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
+  const int n_units = (n_tiles + MC - 1) / MC;
+  const int total = n_units * m_tiles * splits;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int max_clusters = sms / MC;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  const int group_m = m_tiles < 8 ? m_tiles : 8;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * MC);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
+                                     group_m);
+  if (e != cudaSuccess) {
+    b200_set_error("b200_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200_ERR_CUDA;
+  }
+  return b200_check_launch("b200_gemm_bf16");
+}
+
+template <int BLOCK_X, int EPI = 0>
+static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                       int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  // pairs of weight tiles share one multicast activation tile; not worth it for a single tile
+  const bool mc = gemm_multicast_enabled() && n_tiles >= 2;
   CUtensorMap tw, tx;
   int rc = make_tmap_bf16_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBlockW, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X, kBlockK);
+  rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, mc ? BLOCK_X / 2 : BLOCK_X, kBlockK);
   if (rc) return rc;
-  const int n_tiles = (N + kBlockW - 1) / kBlockW;
-  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
-  const int total = n_tiles * m_tiles * splits;
-  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  const int grid = total < sms ? total : sms;
-  const int group_m = m_tiles < 8 ? m_tiles : 8;
-  gemm_bf16_tcgen05_kernel<BLOCK_X, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
-      tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
-  return b200_check_launch("b200_gemm_bf16");
+  if (mc) return launch_gemm_mc<BLOCK_X, EPI, 2>(tw, tx, Y, M, N, K, ldy, out_f32, splits, stream);
+  return launch_gemm_mc<BLOCK_X, EPI, 1>(tw, tx, Y, M, N, K, ldy, out_f32, splits, stream);
 }
 
 }  // namespace b200
