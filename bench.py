@@ -280,6 +280,7 @@ def run_ours(a):
     from gpustack_b200.engine import LLMEngine, TPWorker
     from gpustack_b200.scheduler import SamplingParams
 
+    os.environ.pop("NCCL_DEBUG", None)   # NCCL's version banner goes to stdout; keep it to the JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world != a.gpus:

@@ -118,6 +118,25 @@ int b200_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes)
   return B200_OK;
 }
 
+int b200_dev_malloc(size_t bytes, void** dev_ptr_out) {
+  cudaError_t e = cudaMalloc(dev_ptr_out, bytes);
+  if (e == cudaSuccess) e = cudaMemset(*dev_ptr_out, 0, bytes);
+  if (e != cudaSuccess) {
+    b200_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+int b200_dev_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) {
+    b200_set_error("cudaFree: %s", cudaGetErrorString(e));
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
 int b200_ipc_get_handle(void* dev_ptr, void* handle_out_host) {
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr);

@@ -131,6 +131,10 @@ int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache
 
 /* ---- tensor-parallel all-reduce over NVLink peer memory:
  *      $VLLM/distributed/device_communicators/cuda_communicator.py:241-290 (custom all-reduce) */
+/* Zero-filled device allocation made directly with cudaMalloc (so that it has its own IPC handle;
+ * framework allocators sub-allocate) and its release. */
+int b200_dev_malloc(size_t bytes, void** dev_ptr_out);
+int b200_dev_free(void* dev_ptr);
 int b200_ipc_get_handle(void* dev_ptr, void* handle_out_host /* 64 bytes */);
 int b200_ipc_open_handle(const void* handle_host /* 64 bytes */, void** dev_ptr_out);
 int b200_ipc_close_handle(void* dev_ptr);

@@ -19,7 +19,7 @@ def _port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("allreduce", ["oneshot", "nccl"])
+@pytest.mark.parametrize("allreduce", ["nccl", "oneshot"])
 @pytest.mark.parametrize("eager", ["1", "0"])
 def test_tp_engine_matches_oracle(world, eager, allreduce):
     if torch.cuda.device_count() < world:
