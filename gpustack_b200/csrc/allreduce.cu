@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(512)
 allreduce_add_rms_norm_kernel(PeerPtrs peers, int world, int rank, int flag_blocks,
                               const bf16* __restrict__ residual, const bf16* __restrict__ w,
                               bf16* y, bf16* residual_out, int T, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   __shared__ uint32_t s_epoch;
   uint32_t* my_flags = peers.flags[rank];
@@ -179,7 +181,7 @@ extern "C" int b200_allreduce_add_rms_norm(void* const* peers_host, void* const*
   int threads = (H / 8 + 31) / 32 * 32;
   if (threads > 512) threads = 512;
   const int grid = T < B200_AR_MAX_BLOCKS ? T : B200_AR_MAX_BLOCKS;
-  allreduce_add_rms_norm_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(allreduce_add_rms_norm_kernel, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, 1, 
       pp, world, rank, B200_AR_MAX_BLOCKS, (const bf16*)residual, (const bf16*)w, (bf16*)y,
       (bf16*)residual_out, T, H, eps);
   return b200_check_launch("b200_allreduce_add_rms_norm");

@@ -63,6 +63,8 @@ paged_attn_decode_kernel(const bf16* __restrict__ q, int64_t q_stride,
                          const int32_t* __restrict__ seq_lens, bf16* __restrict__ out,
                          float* __restrict__ ws_o, float* __restrict__ ws_ml, int num_splits,
                          int Hq, int Hkv, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = DecCfg<D>;
   constexpr int KS = D / 16;  // k-steps of QK^T
   constexpr int NT = D / 8;   // n-tiles of PV
@@ -253,6 +255,8 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attn_merge_splits_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml,
                          bf16* __restrict__ out, int num_splits, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -296,6 +300,8 @@ paged_attn_prefill_kernel(const bf16* __restrict__ q, int64_t q_stride,
                           const int32_t* __restrict__ cu_q, const int32_t* __restrict__ ctx_lens,
                           const int32_t* __restrict__ tile_seq, const int32_t* __restrict__ tile_q0,
                           bf16* __restrict__ out, int Hq, int Hkv, int QT, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = PfCfg<D>;
   constexpr int KS = D / 16;
   constexpr int NT = D / 8;
@@ -515,14 +521,14 @@ extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const voi
       if (rc) return rc;
       once = true;
     }
-    paged_attn_decode_kernel<128><<<grid, kDecWarps * 32, DecCfg<128>::kSmemBytes, s>>>(
+    (void)launch_pdl(paged_attn_decode_kernel<128>, dim3(grid), dim3(kDecWarps * 32), DecCfg<128>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
         max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2);
     rc = b200_check_launch("b200_paged_attn_decode");
     if (rc) return rc;
     if (num_splits > 1) {
       const int rows = B * Hq;
-      attn_merge_splits_kernel<128><<<(rows + 3) / 4, 128, 0, s>>>(ws_o, ws_ml, (bf16*)out,
+      (void)launch_pdl(attn_merge_splits_kernel<128>, dim3((rows + 3) / 4), dim3(128), 0, s, 1, ws_o, ws_ml, (bf16*)out,
                                                                   num_splits, rows);
       rc = b200_check_launch("b200_paged_attn_decode(merge)");
     }
@@ -533,14 +539,14 @@ extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const voi
       if (rc) return rc;
       once = true;
     }
-    paged_attn_decode_kernel<64><<<grid, kDecWarps * 32, DecCfg<64>::kSmemBytes, s>>>(
+    (void)launch_pdl(paged_attn_decode_kernel<64>, dim3(grid), dim3(kDecWarps * 32), DecCfg<64>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
         max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2);
     rc = b200_check_launch("b200_paged_attn_decode");
     if (rc) return rc;
     if (num_splits > 1) {
       const int rows = B * Hq;
-      attn_merge_splits_kernel<64><<<(rows + 3) / 4, 128, 0, s>>>(ws_o, ws_ml, (bf16*)out,
+      (void)launch_pdl(attn_merge_splits_kernel<64>, dim3((rows + 3) / 4), dim3(128), 0, s, 1, ws_o, ws_ml, (bf16*)out,
                                                                  num_splits, rows);
       rc = b200_check_launch("b200_paged_attn_decode(merge)");
     }
@@ -580,7 +586,7 @@ extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, const vo
       if (rc) return rc;
       once = true;
     }
-    paged_attn_prefill_kernel<128><<<grid, 32 * G * QT, PfCfg<128>::kSmemBytes, s>>>(
+    (void)launch_pdl(paged_attn_prefill_kernel<128>, dim3(grid), dim3(32 * G * QT), PfCfg<128>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
         max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, (bf16*)out, Hq, Hkv, QT, scale_log2);
   } else {
@@ -590,7 +596,7 @@ extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, const vo
       if (rc) return rc;
       once = true;
     }
-    paged_attn_prefill_kernel<64><<<grid, 32 * G * QT, PfCfg<64>::kSmemBytes, s>>>(
+    (void)launch_pdl(paged_attn_prefill_kernel<64>, dim3(grid), dim3(32 * G * QT), PfCfg<64>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
         max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, (bf16*)out, Hq, Hkv, QT, scale_log2);
   }

@@ -90,6 +90,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel starts with pdl_launch_dependents() (the next kernel in the stream may be scheduled
+// and run its prologue while this one is still executing) and calls pdl_wait() before its first
+// global-memory access (blocks until the preceding kernel has completed and flushed).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

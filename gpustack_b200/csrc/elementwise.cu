@@ -13,6 +13,8 @@ namespace b200 {
 // out[t,i] = bf16(bf16(silu(g)) * u), g = x[t,i], u = x[t,I+i]   ($VLLM activation.py:133-143)
 __global__ void __launch_bounds__(256)
 silu_and_mul_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, int I) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = I >> 3;
   const size_t total = (size_t)T * vec_per_row;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -41,6 +43,8 @@ silu_and_mul_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, i
 __global__ void __launch_bounds__(256)
 embedding_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table,
                  bf16* __restrict__ out, int T, int H, int vocab_start, int vocab_end) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = H >> 3;
   const size_t total = (size_t)T * vec_per_row;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -58,6 +62,8 @@ embedding_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ rows,
                    bf16* __restrict__ out, int n, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = H >> 3;
   const size_t total = (size_t)n * vec_per_row;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -74,6 +80,8 @@ gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ rows,
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ P, int S, bf16* __restrict__ Y, int M, int N,
                      int64_t ldy) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = N >> 2;
   const size_t total = (size_t)M * vec_per_row;
   const size_t plane = (size_t)M * N;
@@ -98,6 +106,8 @@ splitk_reduce_kernel(const float* __restrict__ P, int S, bf16* __restrict__ Y, i
 __global__ void __launch_bounds__(1024)
 argmax_f32_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __restrict__ out_idx,
                   float* __restrict__ out_val, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   const float* row = logits + (size_t)blockIdx.x * ld;
@@ -159,7 +169,7 @@ extern "C" int b200_silu_and_mul(const void* x, void* out, int T, int I, void* s
   B200_REQUIRE(T >= 0 && I > 0 && I % 8 == 0, "silu_and_mul: I=%d must be a multiple of 8", I);
   if (T == 0) return B200_OK;
   const size_t items = (size_t)T * (I / 8);
-  silu_and_mul_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(silu_and_mul_kernel, dim3(ew_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
       (const bf16*)x, (bf16*)out, T, I);
   return b200_check_launch("b200_silu_and_mul");
 }
@@ -169,7 +179,7 @@ extern "C" int b200_embedding(const int32_t* ids, const void* table, void* out, 
   B200_REQUIRE(T >= 0 && H > 0 && H % 8 == 0, "embedding: H=%d must be a multiple of 8", H);
   if (T == 0) return B200_OK;
   const size_t items = (size_t)T * (H / 8);
-  embedding_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(embedding_kernel, dim3(ew_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
       ids, (const bf16*)table, (bf16*)out, T, H, vocab_start, vocab_end);
   return b200_check_launch("b200_embedding");
 }
@@ -179,7 +189,7 @@ extern "C" int b200_gather_rows(const void* x, const int32_t* rows, void* out, i
   B200_REQUIRE(n >= 0 && H > 0 && H % 8 == 0, "gather_rows: H=%d must be a multiple of 8", H);
   if (n == 0) return B200_OK;
   const size_t items = (size_t)n * (H / 8);
-  gather_rows_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(gather_rows_kernel, dim3(ew_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
       (const bf16*)x, rows, (bf16*)out, n, H);
   return b200_check_launch("b200_gather_rows");
 }
@@ -190,7 +200,7 @@ extern "C" int b200_splitk_reduce(const float* partials, int splits, void* Y, in
                "splitk_reduce: N=%d and ldy must be multiples of 4", N);
   if (M == 0) return B200_OK;
   const size_t items = (size_t)M * (N / 4);
-  splitk_reduce_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(splitk_reduce_kernel, dim3(ew_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
       partials, splits, (bf16*)Y, M, N, ldy);
   return b200_check_launch("b200_splitk_reduce");
 }
@@ -199,6 +209,6 @@ extern "C" int b200_argmax_f32(const float* logits, int64_t ld, int32_t* out_idx
                                int B, int V, void* stream) {
   B200_REQUIRE(B >= 0 && V > 0, "argmax: bad shape");
   if (B == 0) return B200_OK;
-  argmax_f32_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(logits, ld, out_idx, out_val, V);
+  (void)launch_pdl(argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx, out_val, V);
   return b200_check_launch("b200_argmax_f32");
 }

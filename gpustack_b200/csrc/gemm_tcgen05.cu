@@ -108,6 +108,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
+  pdl_launch_dependents();  // the next kernel may start its prologue while this one runs
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -131,6 +132,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   if constexpr (MC > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped with the tail
+  // of the previous kernel; from here on we touch its outputs
+  pdl_wait();
 
   const int kb_per_split = (K / kBlockK) / splits;
   // with MC == 2 a "unit" is a PAIR of adjacent weight tiles; this CTA takes tile 2*pair + crank
@@ -299,20 +303,8 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
   const int max_clusters = sms / MC;
   const int clusters = total < max_clusters ? total : max_clusters;
   const int group_m = m_tiles < 8 ? m_tiles : 8;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * MC);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MC;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
-                                     group_m);
+  cudaError_t e = launch_pdl(kernel, dim3(clusters * MC), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, MC,
+                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

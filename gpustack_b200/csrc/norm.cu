@@ -3,6 +3,7 @@
 // Semantics follow $VLLM/ir/ops/layernorm.py:10-58: fp32 statistics over the UNROUNDED sum,
 // normalised value rounded to bf16, then multiplied by the bf16 weight and rounded again.
 #include "common.cuh"
+#include "runtime.h"
 #include "../../include/b200.h"
 
 namespace b200 {
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(512)
 rms_norm_kernel(const bf16* __restrict__ x, const float* __restrict__ partials, int splits,
                 const bf16* __restrict__ residual, const bf16* __restrict__ w,
                 bf16* y, bf16* residual_out, int T, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int nvec = H >> 3;
@@ -126,7 +129,7 @@ extern "C" int b200_rms_norm(const void* x, const void* w, void* y, int T, int H
   if (T == 0) return B200_OK;
   int threads = norm_threads(H);
   // with 512 threads and nvec up to 2048 the per-thread vector count stays <= 4
-  rms_norm_kernel<0><<<T, threads, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rms_norm_kernel<0>, dim3(T), dim3(threads), 0, (cudaStream_t)stream, 1, 
       (const bf16*)x, nullptr, 0, nullptr, (const bf16*)w, (bf16*)y, nullptr, T, H, eps);
   return b200_check_launch("b200_rms_norm");
 }
@@ -138,7 +141,7 @@ extern "C" int b200_fused_add_rms_norm(const void* x, const void* residual, cons
   B200_REQUIRE(residual && residual_out, "fused_add_rms_norm: residual pointers required");
   if (T == 0) return B200_OK;
   int threads = norm_threads(H);
-  rms_norm_kernel<1><<<T, threads, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rms_norm_kernel<1>, dim3(T), dim3(threads), 0, (cudaStream_t)stream, 1, 
       (const bf16*)x, nullptr, 0, (const bf16*)residual, (const bf16*)w, (bf16*)y,
       (bf16*)residual_out, T, H, eps);
   return b200_check_launch("b200_fused_add_rms_norm");
@@ -153,7 +156,7 @@ extern "C" int b200_fused_add_rms_norm_partials(const float* partials, int split
   B200_REQUIRE(splits >= 1 && residual_out, "fused_add_rms_norm_partials: bad arguments");
   if (T == 0) return B200_OK;
   int threads = norm_threads(H);
-  rms_norm_kernel<2><<<T, threads, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rms_norm_kernel<2>, dim3(T), dim3(threads), 0, (cudaStream_t)stream, 1, 
       nullptr, partials, splits, (const bf16*)residual, (const bf16*)w, (bf16*)y,
       (bf16*)residual_out, T, H, eps);
   return b200_check_launch("b200_fused_add_rms_norm_partials");

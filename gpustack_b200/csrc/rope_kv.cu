@@ -4,6 +4,7 @@
 // One CTA per token; each work item is a 16-byte vector (8 bf16).  Rotation is done in fp32 and
 // rounded once (the reference rounds every bf16 op; the difference is < 2 bf16 ulp).
 #include "common.cuh"
+#include "runtime.h"
 #include "../../include/b200.h"
 
 namespace b200 {
@@ -24,6 +25,8 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
                      const bf16* __restrict__ cos_sin, bf16* __restrict__ k_cache,
                      bf16* __restrict__ v_cache, const int32_t* __restrict__ slot_mapping, int Hq,
                      int Hkv, int D, int block_size) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int half = D >> 1;
   const int vec_per_half = half >> 3;           // 16-byte vectors in half a head
@@ -82,7 +85,7 @@ extern "C" int b200_rope_kv_write(void* qkv, const int32_t* positions, const voi
   B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "rope_kv_write: bad shape");
   B200_REQUIRE(D % 16 == 0 && D <= 256, "rope_kv_write: head_dim %d must be a multiple of 16", D);
   if (T == 0) return B200_OK;
-  rope_kv_write_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rope_kv_write_kernel, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, 
       (bf16*)qkv, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache, slot_mapping,
       Hq, Hkv, D, block_size);
   return b200_check_launch("b200_rope_kv_write");

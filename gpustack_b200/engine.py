@@ -144,6 +144,7 @@ class LLMEngine:
                 payload = np.concatenate([s.last_token[:B], s.num_computed[:B], s.block_table[:B].reshape(-1)])
                 self.tp.bcast_step([_KIND_DECODE, B], payload.astype(np.int32))
             toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table)
+            toks = self._apply_sampling(list(s.rows[:B]), toks)
             out = s.update_decode(plan, toks)
             self.step_time["decode"] += time.perf_counter() - t0
         else:
@@ -152,6 +153,7 @@ class LLMEngine:
             if self.tp:
                 self._bcast_prefill(chunks, plan.starts, tables, plan.sample)
             toks = self.runner.prefill(chunks, plan.starts, tables, plan.sample)
+            toks = self._apply_sampling([r for r, smp in zip(plan.reqs, plan.sample) if smp], toks)
             out = self.sched.update_prefill(plan, toks)
             self.step_time["prefill"] += time.perf_counter() - t0
         self.counters["steps"] += 1
@@ -161,6 +163,24 @@ class LLMEngine:
                 self.counters["finished"] += 1
                 self.requests.pop(rid, None)
         return out
+
+    def _apply_sampling(self, reqs, toks):
+        """Override the in-graph greedy tokens of requests that asked for temperature > 0."""
+        rows = [i for i, r in enumerate(reqs) if r.params.temperature > 0.0]
+        if not rows or self.tp is not None:      # TP>1: vocab-sharded logits -> greedy (documented)
+            return toks
+        gens = []
+        for i in rows:
+            r = reqs[i]
+            if r.params.seed is not None and not hasattr(r, "_gen"):
+                r._gen = torch.Generator(device=self.runner.device)
+                r._gen.manual_seed(int(r.params.seed))
+            gens.append(getattr(r, "_gen", None))
+        sampled = self.runner.sample_rows(rows, [reqs[i].params.temperature for i in rows],
+                                          [reqs[i].params.top_p for i in rows], gens)
+        toks = np.array(toks, dtype=np.int32, copy=True)
+        toks[rows] = sampled
+        return toks
 
     def _bcast_prefill(self, chunks, starts, tables, sample) -> None:
         S = len(chunks)

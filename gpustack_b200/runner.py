@@ -63,6 +63,8 @@ class ModelRunner:
         self.num_blocks = 0
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.graph_pool = None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(ecfg.seed)
         self.oneshot = None
         self._ar_toggle = 0
         if self.tp > 1 and tp_ctx is not None and os.environ.get("B200_TP_ALLREDUCE", "oneshot") == "oneshot":
@@ -354,6 +356,35 @@ class ModelRunner:
         self.out_host[:ns].copy_(self.out_ids[:ns], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.out_host[:ns].numpy().copy()
+
+    # ------------------------------------------------------------------------------ sampling
+    def sample_rows(self, rows: Sequence[int], temps: Sequence[float], top_ps: Sequence[float],
+                    generators: Sequence[Optional[torch.Generator]]) -> List[int]:
+        """Temperature / nucleus sampling for the given rows of the last step's logits (the greedy
+        path stays inside the captured graph; sampled rows are overridden afterwards, as
+        $VLLM/v1/sample/sampler.py does with its greedy/random split).  TP>1: logits are
+        vocab-sharded, callers fall back to greedy."""
+        idx = torch.tensor(list(rows), dtype=torch.long, device=self.device)
+        lg = self.logits.index_select(0, idx) / torch.tensor(list(temps), dtype=torch.float32,
+                                                              device=self.device).clamp_min(1e-5).unsqueeze(1)
+        probs = torch.softmax(lg, dim=-1)
+        tp = torch.tensor(list(top_ps), dtype=torch.float32, device=self.device).unsqueeze(1)
+        if bool((tp < 1.0).any()):
+            sp, si = torch.sort(probs, dim=-1, descending=True)
+            keep = (torch.cumsum(sp, dim=-1) - sp) < tp          # always keeps the top token
+            sp = torch.where(keep, sp, torch.zeros_like(sp))
+            probs = torch.zeros_like(probs).scatter_(1, si, sp)
+        probs = probs / probs.sum(dim=-1, keepdim=True)
+        out = [0] * len(generators)
+        shared = [i for i, g in enumerate(generators) if g is None]
+        if shared:   # one batched draw for every row without its own seed
+            draw = torch.multinomial(probs[shared], 1, generator=self._gen).flatten().tolist()
+            for i, t in zip(shared, draw):
+                out[i] = int(t)
+        for i, g in enumerate(generators):
+            if g is not None:
+                out[i] = int(torch.multinomial(probs[i], 1, generator=g))
+        return out
 
     # -------------------------------------------------------------------- test / debug hooks
     def last_logits(self, n: int) -> torch.Tensor:

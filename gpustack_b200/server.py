@@ -45,7 +45,8 @@ def _sampling(body: Dict[str, Any], max_model_len: int, prompt_len: int, tokeniz
         raise ValueError("max_tokens must be at least 1")
     stop_ids = tuple(int(t) for t in (body.get("stop_token_ids") or ()))
     temp = body.get("temperature")
-    return SamplingParams(max_tokens=mt, temperature=0.0 if temp is None else float(temp),
+    # OpenAI / vLLM default: temperature 1.0 when the request does not set it
+    return SamplingParams(max_tokens=mt, temperature=1.0 if temp is None else float(temp),
                           top_p=float(body.get("top_p") or 1.0), ignore_eos=bool(body.get("ignore_eos", False)),
                           stop_token_ids=stop_ids, seed=body.get("seed"))
 

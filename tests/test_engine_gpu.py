@@ -96,3 +96,19 @@ def test_eos_and_stop_handling():
     first = free_run.index(stop_tok)
     assert stopped == free_run[: first + 1]
     assert eng.sched.pool.num_free == eng.sched.pool.num_total   # every block returned
+
+
+def test_temperature_sampling_is_seeded_and_differs_from_greedy():
+    from gpustack_b200.scheduler import SamplingParams
+
+    eng, _ = _engine(O.TINY, enforce_eager=True)
+    g = torch.Generator().manual_seed(8)
+    p = torch.randint(3, 500, (20,), generator=g).tolist()
+    greedy = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True))[0]
+    a = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True, temperature=1.5, seed=123))[0]
+    b = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True, temperature=1.5, seed=123))[0]
+    c = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True, temperature=1.5, seed=7))[0]
+    assert a == b and a != greedy and a != c
+    # top_p -> 0 keeps only the most likely token = greedy
+    d = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True, temperature=1.0, top_p=1e-6, seed=1))[0]
+    assert d == greedy
