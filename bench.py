@@ -217,26 +217,23 @@ def free_port():
 
 
 def run_http_leg(engine, a, mcfg, n_warm, n_timed):
-    """Serve the SAME engine over HTTP from this process (uvicorn thread + engine-core thread) and
-    drive it from a separate client process."""
-    import uvicorn
+    """Serve the SAME engine over HTTP exactly as `b200-engine serve` does -- this process keeps
+    running the engine-core busy loop (on a thread here, bench.py's main thread drives the client),
+    the OpenAI frontend runs in a child process -- and load it from a separate client process."""
+    from gpustack_b200.frontend import spawn_frontend
 
-    from gpustack_b200.async_engine import AsyncEngine
-    from gpustack_b200.server import create_app
-    from gpustack_b200.tokenizer import load_tokenizer
-
-    tok = load_tokenizer(None, mcfg.vocab_size, mcfg.bos_token_id, mcfg.eos_token_id)
-    aeng = AsyncEngine(engine)
-    app = create_app(aeng, tok, "bench-model", engine.ecfg.max_model_len)
     port = free_port()
-    server = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=port, log_level="error", access_log=False,
-                                           backlog=4096))
-    th = threading.Thread(target=server.run, daemon=True)
+    front, core = spawn_frontend(engine, "127.0.0.1", port, "bench-model", None, "error")
+    th = threading.Thread(target=core.run, name="engine-core", daemon=True)
     th.start()
-    for _ in range(200):
-        if server.started:
-            break
-        time.sleep(0.05)
+    import urllib.request
+
+    for _ in range(600):
+        try:
+            if urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1).status == 200:
+                break
+        except Exception:
+            time.sleep(0.1)
     st0 = None
     out = []
     try:
@@ -252,11 +249,9 @@ def run_http_leg(engine, a, mcfg, n_warm, n_timed):
                            text=True, cwd=str(ROOT), timeout=900)
         out = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     finally:
-        server.should_exit = True
-        th.join(timeout=10)
-        aeng._stop = True
-        aeng._wake.set()
-        aeng._thread.join(timeout=10)
+        front.terminate()
+        front.join(timeout=10)
+        th.join(timeout=10)          # the core loop ends when its pipe closes
     st1 = engine.runner.stats
     comp = sum(o["completion_tokens"] for o in out)
     tt = sum(o["total_time_s"] for o in out)
@@ -268,7 +263,8 @@ def run_http_leg(engine, a, mcfg, n_warm, n_timed):
         "p50_ttft_ms": statistics.median(ttft) if ttft else None,
         "p99_ttft_ms": max((o["ttft_ms_p99"] or 0) for o in out) if out else None,
         "successful_requests": sum(o["successful"] for o in out), "requests": sum(o["requests"] for o in out),
-        "path": "HTTP /v1/completions SSE, client in a separate process (host JSON in, host text out)",
+        "path": "HTTP /v1/completions SSE: frontend process <-pipe-> engine core; client in a third process "
+                "(host JSON in, host text out)",
     }
 
 

@@ -66,59 +66,34 @@ class Metrics:
             self.observe("e2e", (st.last_token or st.first_token) - st.arrival)
 
 
-class AsyncEngine:
-    def __init__(self, engine: LLMEngine):
-        self.engine = engine
+class _StreamHub:
+    """Request/stream bookkeeping shared by the in-process (thread) and out-of-process (pipe) engine
+    fronts: per-request asyncio queues, token coalescing, latency metrics."""
+
+    def __init__(self):
         self.metrics = Metrics()
-        self._inbox: "queue.SimpleQueue" = queue.SimpleQueue()
         self._streams: Dict[str, Tuple[asyncio.AbstractEventLoop, asyncio.Queue]] = {}
         self._stats: Dict[str, RequestStats] = {}
         self._ids = itertools.count()
-        self._stop = False
-        self._wake = threading.Event()
         self.errored: Optional[BaseException] = None
-        self._thread = threading.Thread(target=self._loop, name="b200-engine-core", daemon=True)
-        self._thread.start()
 
-    # ------------------------------------------------------------------ engine thread
-    def _loop(self) -> None:
-        eng = self.engine
-        try:
-            while not self._stop:
-                self._drain_inbox()
-                if not eng.has_work():
-                    self._wake.wait(timeout=0.05)
-                    self._wake.clear()
-                    continue
-                out = eng.step()
-                if out is not None and out.req_ids:
-                    self._dispatch(out)
-        except BaseException as e:  # the server turns unhealthy; GPUStack restarts the instance
-            self.errored = e
-            for rid, (loop, q) in list(self._streams.items()):
-                loop.call_soon_threadsafe(q.put_nowait, ([], "error"))
-            raise
+    # -- to be provided by the transport
+    def _submit(self, rid: str, prompt_ids: List[int], params: SamplingParams) -> None:
+        raise NotImplementedError
 
-    def _drain_inbox(self) -> None:
-        while True:
-            try:
-                kind, rid, payload = self._inbox.get_nowait()
-            except queue.Empty:
-                return
-            if kind == "add":
-                prompt_ids, params = payload
-                try:
-                    self.engine.add_request(rid, prompt_ids, params)
-                except Exception as e:  # invalid request: report to the waiting handler
-                    ent = self._streams.get(rid)
-                    if ent:
-                        ent[0].call_soon_threadsafe(ent[1].put_nowait, (e, "invalid"))
-            elif kind == "abort":
-                self.engine.abort_request(rid)
+    def _abort(self, rid: str) -> None:
+        raise NotImplementedError
 
-    def _dispatch(self, out: StepOutput) -> None:
+    def snapshot(self) -> dict:
+        raise NotImplementedError
+
+    def is_healthy(self) -> bool:
+        raise NotImplementedError
+
+    # -- delivery (called from the transport's thread)
+    def _dispatch(self, req_ids, token_ids, finished) -> None:
         by_loop: Dict[asyncio.AbstractEventLoop, List] = {}
-        for rid, tok, fin in zip(out.req_ids, out.token_ids, out.finished):
+        for rid, tok, fin in zip(req_ids, token_ids, finished):
             ent = self._streams.get(rid)
             if ent is not None:
                 by_loop.setdefault(ent[0], []).append((ent[1], tok, fin))
@@ -131,7 +106,16 @@ class AsyncEngine:
         for q, tok, fin in items:
             q.put_nowait(([tok], fin, now))
 
-    # ------------------------------------------------------------------ asyncio side
+    def _fail_request(self, rid: str, exc: Exception) -> None:
+        ent = self._streams.get(rid)
+        if ent:
+            ent[0].call_soon_threadsafe(ent[1].put_nowait, (exc, "invalid"))
+
+    def _fail_all(self) -> None:
+        for rid, (loop, q) in list(self._streams.items()):
+            loop.call_soon_threadsafe(q.put_nowait, ([], "error"))
+
+    # -- asyncio side
     def new_request_id(self, prefix: str = "cmpl") -> str:
         return f"{prefix}-{next(self._ids):08x}{int(time.time() * 1000) & 0xffffff:06x}"
 
@@ -146,8 +130,7 @@ class AsyncEngine:
         self._streams[req_id] = (loop, q)
         st = self._stats[req_id] = RequestStats(arrival=time.monotonic(), prompt_tokens=len(prompt_ids))
         self.metrics.prompt_tokens += len(prompt_ids)
-        self._inbox.put(("add", req_id, (list(prompt_ids), params)))
-        self._wake.set()
+        self._submit(req_id, list(prompt_ids), params)
         finished = None
         try:
             while finished is None:
@@ -171,11 +154,71 @@ class AsyncEngine:
             self._streams.pop(req_id, None)
             self._stats.pop(req_id, None)
             if finished is None:            # client went away
-                self._inbox.put(("abort", req_id, None))
-                self._wake.set()
+                self._abort(req_id)
                 self.metrics.finish(st, "abort")
             else:
                 self.metrics.finish(st, finished)
+
+
+def engine_snapshot(engine) -> dict:
+    s = engine.sched
+    return {"running": s.num_running, "waiting": s.num_waiting, "kv_usage": s.kv_usage(),
+            "preemptions": s.num_preemptions, "generation_tokens": engine.counters["generation_tokens"]}
+
+
+class AsyncEngine(_StreamHub):
+    """Engine core on a background THREAD of the serving process (tests, small deployments)."""
+
+    def __init__(self, engine: LLMEngine):
+        super().__init__()
+        self.engine = engine
+        self._inbox: "queue.SimpleQueue" = queue.SimpleQueue()
+        self._stop = False
+        self._wake = threading.Event()
+        self._thread = threading.Thread(target=self._loop, name="b200-engine-core", daemon=True)
+        self._thread.start()
+
+    def _loop(self) -> None:
+        eng = self.engine
+        try:
+            while not self._stop:
+                self._drain_inbox()
+                if not eng.has_work():
+                    self._wake.wait(timeout=0.05)
+                    self._wake.clear()
+                    continue
+                out = eng.step()
+                if out is not None and out.req_ids:
+                    self._dispatch(out.req_ids, out.token_ids, out.finished)
+        except BaseException as e:  # the server turns unhealthy; GPUStack restarts the instance
+            self.errored = e
+            self._fail_all()
+            raise
+
+    def _drain_inbox(self) -> None:
+        while True:
+            try:
+                kind, rid, payload = self._inbox.get_nowait()
+            except queue.Empty:
+                return
+            if kind == "add":
+                try:
+                    self.engine.add_request(rid, payload[0], payload[1])
+                except Exception as e:  # invalid request: report to the waiting handler
+                    self._fail_request(rid, e)
+            elif kind == "abort":
+                self.engine.abort_request(rid)
+
+    def _submit(self, rid, prompt_ids, params) -> None:
+        self._inbox.put(("add", rid, (prompt_ids, params)))
+        self._wake.set()
+
+    def _abort(self, rid) -> None:
+        self._inbox.put(("abort", rid, None))
+        self._wake.set()
+
+    def snapshot(self) -> dict:
+        return engine_snapshot(self.engine)
 
     def is_healthy(self) -> bool:
         return self.errored is None and self._thread.is_alive()
@@ -185,3 +228,105 @@ class AsyncEngine:
         self._wake.set()
         self._thread.join(timeout=5)
         self.engine.shutdown()
+
+
+# --------------------------------------------------------------------------- process split
+class EngineCoreServer:
+    """Runs in the ENGINE process: the busy loop (schedule -> GPU step -> outputs) fed by a pipe.
+    Counterpart of the reference engine's EngineCoreProc ($VLLM/v1/engine/core.py): the HTTP front
+    lives in another process, so JSON/SSE work never competes with the step loop for the GIL."""
+
+    def __init__(self, engine: LLMEngine, conn):
+        self.engine, self.conn = engine, conn
+
+    def run(self) -> None:
+        eng, conn = self.engine, self.conn
+        last_beat = 0.0
+        try:
+            while True:
+                while conn.poll(0.0 if eng.has_work() else 0.02):
+                    msg = conn.recv()
+                    kind = msg[0]
+                    if kind == "add":
+                        _, rid, prompt_ids, params = msg
+                        try:
+                            eng.add_request(rid, prompt_ids, params)
+                        except Exception as e:  # noqa: BLE001
+                            conn.send(("invalid", rid, str(e)))
+                    elif kind == "abort":
+                        eng.abort_request(msg[1])
+                    elif kind == "shutdown":
+                        return
+                if eng.has_work():
+                    out = eng.step()
+                    if out is not None and out.req_ids:
+                        conn.send(("out", out.req_ids, out.token_ids, out.finished, engine_snapshot(eng)))
+                now = time.monotonic()
+                if now - last_beat > 1.0:
+                    conn.send(("beat", engine_snapshot(eng)))
+                    last_beat = now
+        except (EOFError, BrokenPipeError):
+            return
+        except BaseException as e:  # noqa: BLE001
+            try:
+                conn.send(("died", repr(e)))
+            finally:
+                raise
+
+
+class EngineClient(_StreamHub):
+    """Runs in the FRONTEND process: same interface as AsyncEngine, transport = a pipe to an
+    EngineCoreServer."""
+
+    def __init__(self, conn):
+        super().__init__()
+        self.conn = conn
+        self._send_lock = threading.Lock()
+        self._snap = {"running": 0, "waiting": 0, "kv_usage": 0.0, "preemptions": 0, "generation_tokens": 0}
+        self._last_msg = time.monotonic()
+        self._thread = threading.Thread(target=self._reader, name="b200-engine-client", daemon=True)
+        self._thread.start()
+
+    def _reader(self) -> None:
+        try:
+            while True:
+                msg = self.conn.recv()
+                self._last_msg = time.monotonic()
+                kind = msg[0]
+                if kind == "out":
+                    self._snap = msg[4]
+                    self._dispatch(msg[1], msg[2], msg[3])
+                elif kind == "beat":
+                    self._snap = msg[1]
+                elif kind == "invalid":
+                    self._fail_request(msg[1], ValueError(msg[2]))
+                elif kind == "died":
+                    raise RuntimeError(msg[1])
+        except BaseException as e:  # noqa: BLE001
+            self.errored = e
+            self._fail_all()
+
+    def _send(self, msg) -> None:
+        with self._send_lock:
+            self.conn.send(msg)
+
+    def _submit(self, rid, prompt_ids, params) -> None:
+        self._send(("add", rid, prompt_ids, params))
+
+    def _abort(self, rid) -> None:
+        try:
+            self._send(("abort", rid))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def snapshot(self) -> dict:
+        return dict(self._snap)
+
+    def is_healthy(self) -> bool:
+        return self.errored is None and self._thread.is_alive() and time.monotonic() - self._last_msg < 30.0
+
+    def shutdown(self) -> None:
+        try:
+            self._send(("shutdown",))
+        except Exception:  # noqa: BLE001
+            pass

@@ -118,23 +118,20 @@ def main(argv: Optional[List[str]] = None) -> int:
     ecfg = _engine_config(args, tp)
     workers = _spawn_workers(ecfg, tp) if tp > 1 and "RANK" not in os.environ else []
     try:
-        import uvicorn
-
-        from .async_engine import AsyncEngine
-        from .server import create_app
-        from .tokenizer import load_tokenizer
+        from .frontend import spawn_frontend
 
         eng = make_engine(ecfg)
         name = ecfg.served_model_name or os.path.basename(os.path.normpath(args.model))
-        tok = load_tokenizer(None if args.model.startswith("random:") else args.model, eng.mcfg.vocab_size,
-                             eng.mcfg.bos_token_id, eng.mcfg.eos_token_id)
-        aeng = AsyncEngine(eng)
-        app = create_app(aeng, tok, name, ecfg.max_model_len)
+        model_path = None if args.model.startswith("random:") else args.model
+        # this (GPU-owning) process runs the engine-core busy loop; HTTP lives in a child process
+        front, core = spawn_frontend(eng, args.host, args.port, name, model_path, args.log_level)
         log.info("serving %s on %s:%d (tp=%d, %d KV blocks, max_model_len=%d)", name, args.host, args.port, tp,
                  eng.num_blocks, ecfg.max_model_len)
-        uvicorn.run(app, host=args.host, port=args.port, log_level="warning", access_log=False,
-                    timeout_keep_alive=5, backlog=4096)
-        aeng.shutdown()
+        try:
+            core.run()                      # returns when the frontend goes away / asks to stop
+        finally:
+            eng.shutdown()
+            front.terminate()
     finally:
         for p in workers:
             p.terminate()

@@ -241,7 +241,7 @@ def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_l
 def render_metrics(aeng: AsyncEngine, model: str) -> str:
     """Prometheus exposition with vLLM's metric names so that GPUStack's `vLLM` runtime mapping
     (metrics_config.yaml:74-98) scrapes this engine unchanged."""
-    m, eng = aeng.metrics, aeng.engine
+    m, snap = aeng.metrics, aeng.snapshot()
     lab = f'{{model_name="{model}",engine="0"}}'
     L: List[str] = []
 
@@ -252,13 +252,13 @@ def render_metrics(aeng: AsyncEngine, model: str) -> str:
         L.append(f"# HELP {name} {help_}\n# TYPE {name} counter")
         L.append(f"{name}_total{lab if not extra else extra} {v}")
 
-    gauge("vllm:num_requests_running", "Number of requests in model execution batches.", eng.sched.num_running)
-    gauge("vllm:num_requests_waiting", "Number of requests waiting to be processed.", eng.sched.num_waiting)
-    gauge("vllm:kv_cache_usage_perc", "KV-cache usage. 1 means 100 percent usage.", round(eng.sched.kv_usage(), 6))
-    gauge("vllm:gpu_cache_usage_perc", "KV-cache usage (legacy name).", round(eng.sched.kv_usage(), 6))
-    counter("vllm:num_preemptions", "Cumulative number of preemptions from the engine.", eng.sched.num_preemptions)
+    gauge("vllm:num_requests_running", "Number of requests in model execution batches.", snap["running"])
+    gauge("vllm:num_requests_waiting", "Number of requests waiting to be processed.", snap["waiting"])
+    gauge("vllm:kv_cache_usage_perc", "KV-cache usage. 1 means 100 percent usage.", round(snap["kv_usage"], 6))
+    gauge("vllm:gpu_cache_usage_perc", "KV-cache usage (legacy name).", round(snap["kv_usage"], 6))
+    counter("vllm:num_preemptions", "Cumulative number of preemptions from the engine.", snap["preemptions"])
     counter("vllm:prompt_tokens", "Number of prefill tokens processed.", m.prompt_tokens)
-    counter("vllm:generation_tokens", "Number of generation tokens processed.", eng.counters["generation_tokens"])
+    counter("vllm:generation_tokens", "Number of generation tokens processed.", snap["generation_tokens"])
     L.append("# HELP vllm:request_success Count of successfully processed requests.\n# TYPE vllm:request_success counter")
     for reason, n in m.success.items():
         L.append(f'vllm:request_success_total{{model_name="{model}",engine="0",finished_reason="{reason}"}} {n}')

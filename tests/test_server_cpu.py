@@ -151,3 +151,54 @@ def test_many_concurrent_streams(client):
 
     with cf.ThreadPoolExecutor(16) as ex:
         assert list(ex.map(one, range(32))) == [16] * 32
+
+
+def test_frontend_process_split_streams_over_the_pipe():
+    """`b200-engine serve` topology: engine-core busy loop here (stub GPU), OpenAI frontend in a
+    child process, requests over real HTTP."""
+    import socket
+    import threading
+    import types
+    import urllib.request
+
+    from gpustack_b200.frontend import spawn_frontend
+
+    eng = StubEngine()
+    eng.mcfg = types.SimpleNamespace(vocab_size=600, bos_token_id=1, eos_token_id=2)
+    eng.ecfg = types.SimpleNamespace(max_model_len=512)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    front, core = spawn_frontend(eng, "127.0.0.1", port, "stub-model", None, "error")
+    th = threading.Thread(target=core.run, daemon=True)
+    th.start()
+    try:
+        url = f"http://127.0.0.1:{port}"
+        for _ in range(300):
+            try:
+                if urllib.request.urlopen(url + "/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.1)
+        body = json.dumps({"model": "stub-model", "prompt": [5, 6, 7], "max_tokens": 12, "stream": True,
+                           "ignore_eos": True, "temperature": 0, "stream_options": {"include_usage": True}}).encode()
+        req = urllib.request.Request(url + "/v1/completions", data=body, headers={"content-type": "application/json"})
+        lines = [l.decode().strip() for l in urllib.request.urlopen(req, timeout=30) if l.startswith(b"data: ")]
+        assert lines[-1] == "data: [DONE]"
+        chunks = [json.loads(l[6:]) for l in lines[:-1]]
+        assert "".join(c["choices"][0]["text"] for c in chunks if c["choices"]) == StubEngine.TEXT[:12]
+        assert chunks[-1]["usage"] == {"prompt_tokens": 3, "completion_tokens": 12, "total_tokens": 15}
+        metrics = urllib.request.urlopen(url + "/metrics", timeout=5).read().decode()
+        assert 'vllm:request_success_total{model_name="stub-model",engine="0",finished_reason="length"} 1' in metrics
+        bad = urllib.request.Request(url + "/v1/completions", data=json.dumps(
+            {"model": "stub-model", "prompt": [1] * 600, "max_tokens": 5}).encode(), headers={"content-type": "application/json"})
+        try:
+            urllib.request.urlopen(bad, timeout=10)
+            assert False, "expected HTTP 400"
+        except urllib.error.HTTPError as e:
+            assert e.code == 400
+    finally:
+        front.terminate()
+        front.join(timeout=10)
+        th.join(timeout=10)
+    assert not th.is_alive()
