@@ -363,6 +363,10 @@ def run_ours(a):
         "gemm_decode_live": {"launches": gd["launches"], "ms": gd["ms"],
                              "gbs": gd["bytes"] / (gd["ms"] * 1e-3) / 1e9 if gd["ms"] else None},
         "event_ms_total": ev_ms, "init_s": init_s, "kv_blocks": engine.num_blocks,
+        "decode_step_breakdown_ms": {
+            "wall": dtime / max(1, dsteps) * 1e3,
+            "h2d+graph+sync": (st1.get("decode_gpu_s", 0.0) - st0.get("decode_gpu_s", 0.0)) / max(1, dsteps) * 1e3,
+            "tp_step_broadcast": (stime1.get("decode_bcast", 0.0) - stime0.get("decode_bcast", 0.0)) / max(1, dsteps) * 1e3},
     }
     if not a.no_e2e:
         try:

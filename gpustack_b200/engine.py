@@ -141,8 +141,10 @@ class LLMEngine:
             B = plan.batch
             s = self.sched
             if self.tp:
+                tb = time.perf_counter()
                 payload = np.concatenate([s.last_token[:B], s.num_computed[:B], s.block_table[:B].reshape(-1)])
                 self.tp.bcast_step([_KIND_DECODE, B], payload.astype(np.int32))
+                self.step_time["decode_bcast"] = self.step_time.get("decode_bcast", 0.0) + time.perf_counter() - tb
             toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table)
             toks = self._apply_sampling(list(s.rows[:B]), toks)
             out = s.update_decode(plan, toks)

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import math
 import os
+import time
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -274,6 +275,7 @@ class ModelRunner:
             st[self.d_lens + B:self.d_lens + Bp] = 0
         st[self.d_bt:self.d_bt + B * self.max_blocks] = block_table[:B].reshape(-1)
         n = self.d_bt + B * self.max_blocks
+        t_gpu = time.perf_counter()
         self.stage_dev[:n].copy_(self.stage_host[:n], non_blocking=True)
         if self.graphs:
             self.graphs[Bp].replay()
@@ -283,6 +285,7 @@ class ModelRunner:
             self._decode_forward(Bp)
         self.out_host[:B].copy_(self.out_ids[:B], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self.stats["decode_gpu_s"] = self.stats.get("decode_gpu_s", 0.0) + time.perf_counter() - t_gpu
         self.stats["decode_steps"] += 1
         self.stats["h2d_bytes"] += n * 4
         self.stats["d2h_bytes"] += B * 4

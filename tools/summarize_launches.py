@@ -16,7 +16,11 @@ def main(path, detail=False):
     with open(path) as f:
         rows = list(csv.DictReader([l for l in f if not l.startswith("==")]))
     idx = [i for i, r in enumerate(rows) if "embedding_kernel" in r["Kernel Name"]]
-    regions = {"prefill step (16 x 512 = 8192 tokens)": rows[idx[0]:idx[1]], "decode step (B=256, ctx~516)": rows[idx[1]:]}
+    if len(idx) >= 2:
+        regions = {"prefill step (16 x 512 = 8192 tokens)": rows[idx[0]:idx[1]],
+                   "decode step (B=256, ctx~516)": rows[idx[1]:]}
+    else:
+        regions = {"decode step (B=256, ctx~516)": rows[idx[0]:]}
     for title, rs in regions.items():
         agg, tot = collections.OrderedDict(), 0.0
         for r in rs:
