@@ -20,8 +20,30 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
+// PARTIALS = true: the QKV projection arrives as `splits` fp32 split-K partial sums
+// [splits][T][(Hq+2Hkv)*D]; they are summed, rounded to bf16 (what the un-split GEMM would have
+// stored) and then rotated -- the split-K reduction costs no extra pass.
+__device__ __forceinline__ void load8(const bf16* qkv, const float* partials, int splits, size_t plane,
+                                      size_t off, float (&f)[8]) {
+  if (partials == nullptr) {
+    unpack8(ld_v4(qkv + off), f);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float4* p = reinterpret_cast<const float4*>(partials + (size_t)s * plane + off);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+    f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j]);
+}
+
 __global__ void __launch_bounds__(256)
-rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positions,
+rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials, int splits, int T,
+                     const int32_t* __restrict__ positions,
                      const bf16* __restrict__ cos_sin, bf16* __restrict__ k_cache,
                      bf16* __restrict__ v_cache, const int32_t* __restrict__ slot_mapping, int Hq,
                      int Hkv, int D, int block_size) {
@@ -35,6 +57,7 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
   const int pos = positions[t];
   const int slot = slot_mapping[t];
   const size_t row = (size_t)t * (size_t)(Hq + 2 * Hkv) * D;
+  const size_t plane = (size_t)T * (size_t)(Hq + 2 * Hkv) * D;
   const bf16* cs = cos_sin + (size_t)pos * D;
   const int blk = slot >= 0 ? slot / block_size : 0;
   const int off = slot >= 0 ? slot % block_size : 0;
@@ -46,8 +69,8 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
       bf16* p1 = qkv + row + (size_t)head * D + vi * 8;
       bf16* p2 = p1 + half;
       float x1[8], x2[8], c[8], s[8], o1[8], o2[8];
-      unpack8(ld_v4(p1), x1);
-      unpack8(ld_v4(p2), x2);
+      load8(qkv, partials, splits, plane, (size_t)(p1 - qkv), x1);
+      load8(qkv, partials, splits, plane, (size_t)(p2 - qkv), x2);
       unpack8(ld_v4(cs + vi * 8), c);
       unpack8(ld_v4(cs + half + vi * 8), s);
 #pragma unroll
@@ -64,13 +87,21 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
         st_v4(kc, r1);
         st_v4(kc + half, r2);
       }
-    } else if (slot >= 0) {
+    } else if (slot >= 0 || partials != nullptr) {
       const int j = it - rope_items;
       const int vh = j / (D >> 3);
       const int vi = j % (D >> 3);
-      const bf16* src = qkv + row + (size_t)(Hq + Hkv + vh) * D + vi * 8;
+      const size_t voff = row + (size_t)(Hq + Hkv + vh) * D + vi * 8;
       bf16* dst = v_cache + (((size_t)blk * Hkv + vh) * block_size + off) * D + vi * 8;
-      st_v4(dst, ld_v4(src));
+      if (partials == nullptr) {
+        st_v4(dst, ld_v4(qkv + voff));
+      } else {
+        float vf[8];
+        load8(qkv, partials, splits, plane, voff, vf);
+        const uint4 vv = pack8(vf);
+        if (slot >= 0) st_v4(dst, vv);
+        st_v4(qkv + voff, vv);
+      }
     }
   }
 }
@@ -79,14 +110,30 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
 
 using namespace b200;
 
+static int rope_launch(void* qkv, const float* partials, int splits, const int32_t* positions,
+                       const void* cos_sin, void* k_cache, void* v_cache, const int32_t* slot_mapping,
+                       int T, int Hq, int Hkv, int D, int block_size, void* stream, const char* what) {
+  B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "%s: bad shape", what);
+  B200_REQUIRE(D % 16 == 0 && D <= 256, "%s: head_dim %d must be a multiple of 16", what, D);
+  if (T == 0) return B200_OK;
+  (void)launch_pdl(rope_kv_write_kernel, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
+                   partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
+                   slot_mapping, Hq, Hkv, D, block_size);
+  return b200_check_launch(what);
+}
+
 extern "C" int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin,
                                   void* k_cache, void* v_cache, const int32_t* slot_mapping, int T,
                                   int Hq, int Hkv, int D, int block_size, void* stream) {
-  B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "rope_kv_write: bad shape");
-  B200_REQUIRE(D % 16 == 0 && D <= 256, "rope_kv_write: head_dim %d must be a multiple of 16", D);
-  if (T == 0) return B200_OK;
-  (void)launch_pdl(rope_kv_write_kernel, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, 
-      (bf16*)qkv, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache, slot_mapping,
-      Hq, Hkv, D, block_size);
-  return b200_check_launch("b200_rope_kv_write");
+  return rope_launch(qkv, nullptr, 0, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq, Hkv, D,
+                     block_size, stream, "b200_rope_kv_write");
+}
+
+extern "C" int b200_rope_kv_write_partials(const float* partials, int splits, void* qkv_out,
+                                           const int32_t* positions, const void* cos_sin, void* k_cache,
+                                           void* v_cache, const int32_t* slot_mapping, int T, int Hq,
+                                           int Hkv, int D, int block_size, void* stream) {
+  B200_REQUIRE(partials != nullptr && splits >= 1, "rope_kv_write_partials: partials required");
+  return rope_launch(qkv_out, partials, splits, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq,
+                     Hkv, D, block_size, stream, "b200_rope_kv_write_partials");
 }

@@ -61,6 +61,14 @@ int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin,
                        void* v_cache, const int32_t* slot_mapping, int T, int Hq, int Hkv, int D,
                        int block_size, void* stream);
 
+/* Same, with the QKV projection arriving as `splits` fp32 split-K partial sums
+ * [splits][T][(Hq+2Hkv)*D]: they are summed and rounded to bf16 (what the un-split GEMM would have
+ * stored), rotated, written to qkv_out (bf16, same layout) and scattered into the cache. */
+int b200_rope_kv_write_partials(const float* partials, int splits, void* qkv_out,
+                                const int32_t* positions, const void* cos_sin, void* k_cache,
+                                void* v_cache, const int32_t* slot_mapping, int T, int Hq, int Hkv,
+                                int D, int block_size, void* stream);
+
 /* ---- activation: $VLLM/model_executor/layers/activation.py:133-143 ----------------------- */
 /* out[t, i] = bf16(bf16(silu(x[t, i])) * x[t, I + i]);  x [T, 2I] bf16, out [T, I] bf16. */
 int b200_silu_and_mul(const void* x, void* out, int T, int I, void* stream);

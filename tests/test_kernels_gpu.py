@@ -119,6 +119,27 @@ def test_rope_kv_write(ops, Hq, Hkv, D, out_dir):
             assert float(kcc[s // bs, :, s % bs].abs().sum()) == 0.0
 
 
+def test_rope_kv_write_from_splitk_partials(ops, out_dir):
+    """split-K QKV partials reduced inside the RoPE kernel == reduce-to-bf16 then RoPE."""
+    g = torch.Generator().manual_seed(77)
+    T, Hq, Hkv, D, S, nblk = 21, 32, 8, 128, 4, 8
+    W = (Hq + 2 * Hkv) * D
+    parts = torch.randn(S, T, W, generator=g) * 0.5
+    pos = torch.randint(0, 400, (T,), generator=g, dtype=torch.int32)
+    cache = O.cos_sin_cache(D, 512, 500000.0)
+    slots = torch.randperm(nblk * 16, generator=g)[:T].to(torch.int32); slots[5] = -1
+    kc1 = torch.zeros(nblk, Hkv, 16, D, dtype=BF, device="cuda"); vc1 = torch.zeros_like(kc1)
+    kc2 = torch.zeros_like(kc1); vc2 = torch.zeros_like(kc1)
+    acc = parts[0].clone()
+    for s_ in range(1, S):
+        acc = acc + parts[s_]          # same sequential fp32 order as the kernel
+    ref_qkv = acc.to(BF).cuda()
+    ops.rope_kv_write(ref_qkv, pos.cuda(), cache.cuda(), kc1, vc1, slots.cuda(), Hq, Hkv, D)
+    out = torch.empty(T, W, dtype=BF, device="cuda")
+    ops.rope_kv_write_partials(parts.cuda(), out, pos.cuda(), cache.cuda(), kc2, vc2, slots.cuda(), Hq, Hkv, D)
+    assert torch.equal(out, ref_qkv) and torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+
+
 @pytest.mark.parametrize("T,I", [(1, 14336), (65, 14336), (9, 4864), (300, 1024)])
 def test_silu_and_mul(ops, T, I, out_dir):
     g = torch.Generator().manual_seed(I)
