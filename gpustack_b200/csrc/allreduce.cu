@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 __device__ __forceinline__ uint4 ld_peer_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p)
                : "memory");
@@ -53,8 +53,25 @@ __device__ __forceinline__ float ar_block_sum(float v, float* red) {
   return warp_sum(t);
 }
 
-// flags layout on every rank: [gridDim.x][world] arrival words followed by [gridDim.x] private
-// per-CTA epoch counters (only ever touched by the owning rank).
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// flags layout on every rank (uint32 words):
+//   [0, world)            arrival words, written by the peers (word r = rank r's epoch)
+//   [world]               local "go" word, written by CTA 0 once every peer has arrived
+//   [world+1, +grid)      private per-CTA call counters (every launch uses the SAME fixed grid, so
+//                         all of them equal the call epoch; kept on the device so that CUDA-graph
+//                         replays need no host-side epoch)
+// Only CTA 0 talks to the other GPUs (one system-scope release/acquire handshake per call); the
+// other CTAs wait on the local go word at GPU scope.  The release/acquire chain
+// peer GEMM -> peer signal -> CTA 0 acquire.sys -> go release.gpu -> CTA acquire.gpu
+// makes the peers' partial sums visible to every CTA.
 __global__ void __launch_bounds__(512)
 allreduce_add_rms_norm_kernel(PeerPtrs peers, int world, int rank, int flag_blocks,
                               const bf16* __restrict__ residual, const bf16* __restrict__ w,
@@ -62,32 +79,50 @@ allreduce_add_rms_norm_kernel(PeerPtrs peers, int world, int rank, int flag_bloc
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
-  __shared__ uint32_t s_epoch;
   uint32_t* my_flags = peers.flags[rank];
+  uint32_t* go = my_flags + world;
+  uint32_t epoch = 0;
   if (threadIdx.x == 0) {
-    uint32_t* ctr = my_flags + (size_t)flag_blocks * world + blockIdx.x;
-    const uint32_t e = *ctr + 1;
-    *ctr = e;
-    s_epoch = e;
-    __threadfence_system();
+    uint32_t* ctr = my_flags + world + 1 + blockIdx.x;
+    epoch = *ctr + 1;
+    *ctr = epoch;
   }
-  __syncthreads();
-  const uint32_t epoch = s_epoch;
-  if (threadIdx.x < world) {
-    st_release_sys(peers.flags[threadIdx.x] + (size_t)blockIdx.x * world + rank, epoch);
-    const uint32_t* mine = my_flags + (size_t)blockIdx.x * world + threadIdx.x;
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-      if ((++spins & 1023u) == 0) {
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 10000000000ull) __trap();  // a peer never arrived: fail loudly
+  if (blockIdx.x == 0) {
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = epoch;
+    __syncthreads();
+    epoch = s_epoch;
+    if (threadIdx.x < world) {
+      if ((int)threadIdx.x != rank) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
+      const uint32_t* mine = my_flags + threadIdx.x;
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+      while ((int)threadIdx.x != rank && (int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        if ((++spins & 1023u) == 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) __trap();  // a peer never arrived: fail loudly
+        }
       }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(go, epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+      while ((int32_t)(ld_acquire_gpu(go) - epoch) < 0) {
+        if ((++spins & 4095u) == 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) __trap();
+        }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int nvec = H >> 3;
   for (int row = blockIdx.x; row < T; row += gridDim.x) {
@@ -156,11 +191,11 @@ allreduce_add_rms_norm_kernel(PeerPtrs peers, int world, int rank, int flag_bloc
 
 using namespace b200;
 
-// Number of CTAs the kernel is launched with for T rows; flag arrays must hold
-// B200_AR_MAX_BLOCKS * (world + 1) uint32 words.
-#define B200_AR_MAX_BLOCKS 256
+// The kernel is ALWAYS launched with this many CTAs (rows are looped), so that the private
+// per-CTA call counters stay equal to the call epoch.
+#define B200_AR_BLOCKS 128
 
-extern "C" int b200_allreduce_flag_words(int world) { return B200_AR_MAX_BLOCKS * (world + 1); }
+extern "C" int b200_allreduce_flag_words(int world) { return world + 1 + B200_AR_BLOCKS + 32; }
 
 extern "C" int b200_allreduce_add_rms_norm(void* const* peers_host, void* const* flags_host,
                                            int world, int rank, uint32_t epoch_unused,
@@ -180,9 +215,9 @@ extern "C" int b200_allreduce_add_rms_norm(void* const* peers_host, void* const*
   }
   int threads = (H / 8 + 31) / 32 * 32;
   if (threads > 512) threads = 512;
-  const int grid = T < B200_AR_MAX_BLOCKS ? T : B200_AR_MAX_BLOCKS;
+  const int grid = B200_AR_BLOCKS;
   (void)launch_pdl(allreduce_add_rms_norm_kernel, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, 1, 
-      pp, world, rank, B200_AR_MAX_BLOCKS, (const bf16*)residual, (const bf16*)w, (bf16*)y,
+      pp, world, rank, B200_AR_BLOCKS, (const bf16*)residual, (const bf16*)w, (bf16*)y,
       (bf16*)residual_out, T, H, eps);
   return b200_check_launch("b200_allreduce_add_rms_norm");
 }

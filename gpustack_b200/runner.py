@@ -143,7 +143,8 @@ class ModelRunner:
         eps = self.mcfg.rms_norm_eps
         if self.tp > 1:
             ar = self.oneshot
-            if ar is not None and T <= ar.max_tokens:
+            # one-shot moves (tp-1) x the message over NVLink: right for decode-sized messages only
+            if ar is not None and T <= ar.max_tokens and T * self.H * 2 * (self.tp - 1) <= (4 << 20):
                 # GEMM writes its partial into a peer-mapped staging buffer; ONE kernel then pulls
                 # every rank's partial over NVLink, sums, adds the residual and normalises.
                 which = self._ar_toggle
