@@ -77,6 +77,53 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
   return c;
 }
 
+// TMEM accumulator (this warp's 32 lanes x BLOCK_X columns) -> global memory.
+// EPI 0: bf16 / fp32 store; EPI 1: SiLU*mul of interleaved gate/up rows (see the kernel comment).
+template <int BLOCK_X, int EPI>
+__device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, size_t split_off, int n,
+                                                    int m_base, int M, int N, int64_t ldy, int out_f32,
+                                                    int lane) {
+  bf16* Yb = reinterpret_cast<bf16*>(Yv);
+  float* Yf = reinterpret_cast<float*>(Yv);
+  constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_X; c0 += CH) {
+    if (m_base + c0 >= M) break;  // warp-uniform: rest of the tile is padding
+    uint32_t r[CH];
+    if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, r);
+    else tmem_ld_32x16(t_addr + c0, r);
+    tmem_ld_wait();
+    if constexpr (EPI == 1) {
+      const int ch = n >> 1;          // output channel of this lane pair
+      bf16* dst = Yb + (size_t)(m_base + c0) * ldy + ch;
+      const bool odd = lane & 1;
+#pragma unroll
+      for (int j = 0; j < CH; j += 2) {
+        // even lane (gate row) computes token j, odd lane (up row) computes token j+1
+        const uint32_t send = odd ? r[j] : r[j + 1];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        const float g = round_bf16(__uint_as_float(odd ? recv : r[j]));
+        const float up = round_bf16(__uint_as_float(odd ? r[j + 1] : recv));
+        const float sg = round_bf16(g / (1.f + __expf(-g)));
+        const int m = m_base + c0 + j + (odd ? 1 : 0);
+        if (n < N && m < M) dst[(size_t)(j + (odd ? 1 : 0)) * ldy] = __float2bfloat16_rn(sg * up);
+      }
+    } else if (n < N) {
+      if (out_f32) {
+        float* dst = Yf + split_off + (size_t)(m_base + c0) * ldy + n;
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __uint_as_float(r[j]);
+      } else {
+        bf16* dst = Yb + (size_t)(m_base + c0) * ldy + n;
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __float2bfloat16_rn(__uint_as_float(r[j]));
+      }
+    }
+  }
+}
+
 // EPI 0: store the accumulator (bf16, or fp32 / split-K partials).
 // EPI 1: SiLU*mul epilogue for the gate_up projection ($VLLM activation.py:133-143 fused into the
 //        producing GEMM): W rows are interleaved (row 2i = gate_i, row 2i+1 = up_i), so the two
@@ -208,8 +255,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    bf16* Yb = reinterpret_cast<bf16*>(Yv);
-    float* Yf = reinterpret_cast<float*>(Yv);
     for (int u = first_unit; u < total_units; u += unit_stride) {
       const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
       mbar_wait_guarded(&tmem_full[acc], acc_phase);
@@ -218,43 +263,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
       const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
-      constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_X; c0 += CH) {
-        if (m_base + c0 >= M) break;  // warp-uniform: rest of the tile is padding
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, r);
-        else tmem_ld_32x16(t_addr + c0, r);
-        tmem_ld_wait();
-        if constexpr (EPI == 1) {
-          const int ch = n >> 1;          // output channel of this lane pair
-          bf16* dst = Yb + (size_t)(m_base + c0) * ldy + ch;
-          const bool odd = lane & 1;
-#pragma unroll
-          for (int j = 0; j < CH; j += 2) {
-            // even lane (gate row) computes token j, odd lane (up row) computes token j+1
-            const uint32_t send = odd ? r[j] : r[j + 1];
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float g = round_bf16(__uint_as_float(odd ? recv : r[j]));
-            const float up = round_bf16(__uint_as_float(odd ? r[j + 1] : recv));
-            const float sg = round_bf16(g / (1.f + __expf(-g)));
-            const int m = m_base + c0 + j + (odd ? 1 : 0);
-            if (n < N && m < M) dst[(size_t)(j + (odd ? 1 : 0)) * ldy] = __float2bfloat16_rn(sg * up);
-          }
-        } else if (n < N) {
-          if (out_f32) {
-            float* dst = Yf + split_off + (size_t)(m_base + c0) * ldy + n;
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __uint_as_float(r[j]);
-          } else {
-            bf16* dst = Yb + (size_t)(m_base + c0) * ldy + n;
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __float2bfloat16_rn(__uint_as_float(r[j]));
-          }
-        }
-      }
+      epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -268,6 +277,161 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =================================================================================================
+// 2-SM variant (tcgen05.mma.cta_group::2): a CTA PAIR computes one 256 (weight rows) x BLOCK_X
+// (tokens) tile.  Each CTA stages its own 128 weight rows and HALF of the activation tile; the
+// pair's tensor cores read both halves, so per SM the shared-memory operand traffic of a k-block
+// drops from 16 KB + BLOCK_X*128 B to 16 KB + BLOCK_X*64 B and the ring gets deeper.  The leader
+// (cluster rank 0) issues every MMA; data arrival from both CTAs is tracked on the leader's full
+// barriers (TMA .cta_group::2 + remote expect_tx), stage release and accumulator hand-off are
+// multicast commits to both CTAs, and both CTAs' epilogue warps release the accumulator on the
+// leader's barrier.
+template <int BLOCK_X>
+struct Gemm2Cfg {
+  static constexpr int kHalf = BLOCK_X / 2;
+  static constexpr int kABytes = kBlockW * kBlockK * 2;
+  static constexpr int kBBytes = kHalf * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 10 ? 10 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_X < 32 ? 32 : 2 * BLOCK_X;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_X, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
+                             int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
+                             int m_tiles, int group_m) {
+  using Cfg = Gemm2Cfg<BLOCK_X>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  pdl_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);   // (leader's copy is the live one) one expect_tx arrive per CTA
+      mbar_init(&empty_bar[i], 1);  // one multicast commit from the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);   // multicast commit from the leader
+      mbar_init(&tmem_empty[i], 8);  // (leader's copy) 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int kb_per_split = (K / kBlockK) / splits;
+  const int n_units = (n_tiles + 1) / 2;  // a unit = a pair of adjacent weight tiles (256 rows)
+  const int total_units = n_units * m_tiles * splits;
+  const int first_unit = (int)(blockIdx.x / 2);
+  const int unit_stride = (int)(gridDim.x / 2);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      const uint64_t hint_w = (m_tiles > 1) ? kEvictNormal : kEvictFirst;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = first_unit; u < total_units; u += unit_stride) {
+        const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
+        const int n_tile = c.n_tile * 2 + (int)crank;
+        const int k0 = c.split * kb_per_split * kBlockK;
+        for (int kb = 0; kb < kb_per_split; ++kb) {
+          mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+          uint8_t* a = smem + stage * Cfg::kStageBytes;
+          uint8_t* b = a + Cfg::kABytes;
+          // this CTA's bytes are announced on the LEADER's barrier, where the TMAs complete
+          mbar_expect_tx_cluster(mapa_u32(&full_bar[stage], 0), Cfg::kStageBytes);
+          tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kBlockK, n_tile * kBlockW, hint_w);
+          tma_load_2d_2sm(b, &tmap_x, &full_bar[stage], k0 + kb * kBlockK,
+                          c.m_tile * BLOCK_X + (int)crank * Cfg::kHalf, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockW, BLOCK_X);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = first_unit; u < total_units; u += unit_stride) {
+        mbar_wait_guarded(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_X);
+        for (int kb = 0; kb < kb_per_split; ++kb) {
+          mbar_wait_guarded(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                          umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm_mc(&empty_bar[stage], 3);  // both CTAs' slots are free once these retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_mc(&tmem_full[acc], 3);      // accumulator complete in both CTAs' TMEM
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = first_unit; u < total_units; u += unit_stride) {
+      const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
+      mbar_wait_guarded(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int n = (c.n_tile * 2 + (int)crank) * kBlockW + quad * 32 + lane;
+      const int m_base = c.m_tile * BLOCK_X;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
+      const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
+      epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -313,10 +477,58 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
   return b200_check_launch("b200_gemm_bf16");
 }
 
+static bool gemm_2sm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_2SM");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <int BLOCK_X, int EPI>
+static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                           int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BLOCK_X>;
+  auto kernel = gemm_bf16_tcgen05_2sm_kernel<BLOCK_X, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      b200_set_error("gemm(2sm): cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return B200_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_tmap_bf16_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBlockW, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
+  if (rc) return rc;
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
+  const int total = ((n_tiles + 1) / 2) * m_tiles * splits;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int clusters = total < sms / 2 ? total : sms / 2;
+  const int group_m = m_tiles < 8 ? m_tiles : 8;
+  cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
+                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
+  if (e != cudaSuccess) {
+    b200_set_error("b200_gemm_bf16(2sm): launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200_ERR_CUDA;
+  }
+  return b200_check_launch("b200_gemm_bf16(2sm)");
+}
+
 template <int BLOCK_X, int EPI = 0>
 static int launch_gemm(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
                        int64_t ldw, int64_t ldy, int out_f32, int splits, cudaStream_t stream) {
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  if constexpr (BLOCK_X >= 32) {
+    if (gemm_2sm_enabled() && n_tiles >= 2)
+      return launch_gemm_2sm<BLOCK_X, EPI>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, stream);
+  }
   // pairs of weight tiles share one multicast activation tile; not worth it for a single tile
   const bool mc = gemm_multicast_enabled() && n_tiles >= 2;
   CUtensorMap tw, tx;
