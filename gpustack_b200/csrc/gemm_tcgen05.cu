@@ -480,8 +480,8 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
 static bool gemm_2sm_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("B200_GEMM_2SM");
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("B200_GEMM_2SM");   // default on; B200_GEMM_2SM=0 falls back to 1-CTA tiles
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
 }
