@@ -477,6 +477,17 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
   return b200_check_launch("b200_gemm_bf16");
 }
 
+// m-tiles per raster group: a group's activation tiles stay L2-resident while the weight matrix
+// streams past once per group (B200_GEMM_GROUP_M overrides for experiments).
+static int gemm_group_m(int m_tiles) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_GROUP_M");
+    v = (e && atoi(e) > 0) ? atoi(e) : 16;   // measured: 16 > 8 > 32 on the 8B prefill shapes
+  }
+  return m_tiles < v ? m_tiles : v;
+}
+
 static bool gemm_2sm_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -510,7 +521,7 @@ static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, 
   const int total = ((n_tiles + 1) / 2) * m_tiles * splits;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
-  const int group_m = m_tiles < 8 ? m_tiles : 8;
+  const int group_m = gemm_group_m(m_tiles);
   cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
                              tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
   if (e != cudaSuccess) {

@@ -23,9 +23,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // PARTIALS = true: the QKV projection arrives as `splits` fp32 split-K partial sums
 // [splits][T][(Hq+2Hkv)*D]; they are summed, rounded to bf16 (what the un-split GEMM would have
 // stored) and then rotated -- the split-K reduction costs no extra pass.
+template <bool PARTIALS>
 __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, int splits, size_t plane,
                                       size_t off, float (&f)[8]) {
-  if (partials == nullptr) {
+  if constexpr (!PARTIALS) {
     unpack8(ld_v4(qkv + off), f);
     return;
   }
@@ -41,6 +42,7 @@ __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, in
   for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j]);
 }
 
+template <bool PARTIALS>
 __global__ void __launch_bounds__(256)
 rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials, int splits, int T,
                      const int32_t* __restrict__ positions,
@@ -69,8 +71,8 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials,
       bf16* p1 = qkv + row + (size_t)head * D + vi * 8;
       bf16* p2 = p1 + half;
       float x1[8], x2[8], c[8], s[8], o1[8], o2[8];
-      load8(qkv, partials, splits, plane, (size_t)(p1 - qkv), x1);
-      load8(qkv, partials, splits, plane, (size_t)(p2 - qkv), x2);
+      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p1 - qkv), x1);
+      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p2 - qkv), x2);
       unpack8(ld_v4(cs + vi * 8), c);
       unpack8(ld_v4(cs + half + vi * 8), s);
 #pragma unroll
@@ -87,17 +89,17 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials,
         st_v4(kc, r1);
         st_v4(kc + half, r2);
       }
-    } else if (slot >= 0 || partials != nullptr) {
+    } else if (slot >= 0 || PARTIALS) {
       const int j = it - rope_items;
       const int vh = j / (D >> 3);
       const int vi = j % (D >> 3);
       const size_t voff = row + (size_t)(Hq + Hkv + vh) * D + vi * 8;
       bf16* dst = v_cache + (((size_t)blk * Hkv + vh) * block_size + off) * D + vi * 8;
-      if (partials == nullptr) {
+      if constexpr (!PARTIALS) {
         st_v4(dst, ld_v4(qkv + voff));
       } else {
         float vf[8];
-        load8(qkv, partials, splits, plane, voff, vf);
+        load8<true>(qkv, partials, splits, plane, voff, vf);
         const uint4 vv = pack8(vf);
         if (slot >= 0) st_v4(dst, vv);
         st_v4(qkv + voff, vv);
@@ -116,9 +118,14 @@ static int rope_launch(void* qkv, const float* partials, int splits, const int32
   B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "%s: bad shape", what);
   B200_REQUIRE(D % 16 == 0 && D <= 256, "%s: head_dim %d must be a multiple of 16", what, D);
   if (T == 0) return B200_OK;
-  (void)launch_pdl(rope_kv_write_kernel, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
-                   partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
-                   slot_mapping, Hq, Hkv, D, block_size);
+  if (partials != nullptr)
+    (void)launch_pdl(rope_kv_write_kernel<true>, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
+                     partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
+                     slot_mapping, Hq, Hkv, D, block_size);
+  else
+    (void)launch_pdl(rope_kv_write_kernel<false>, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
+                     partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
+                     slot_mapping, Hq, Hkv, D, block_size);
   return b200_check_launch(what);
 }
 
