@@ -19,6 +19,7 @@
 #include "../../include/b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -464,6 +465,191 @@ paged_attn_prefill_kernel(const bf16* __restrict__ q, int64_t q_stride,
   }
 }
 
+// ----------------------------------------------------------------------------- prefill, v2
+// Same tiling as above (CTA = 16*QT query tokens x G heads, one warp per 16x1), restructured for
+// occupancy: Q fragments are re-read from (swizzled) shared memory instead of living in 32
+// registers, K/V stream in 32-token chunks through a 3-stage cp.async ring with ONE barrier per
+// chunk, and the kernel fits 128 registers so two CTAs share an SM (16 warps instead of 8).
+constexpr int kPf2Chunk = 32;
+constexpr int kPf2Stages = 3;
+
+template <int D>
+struct Pf2Cfg {
+  static constexpr int kQWarpBytes = 16 * D * 2;               // one warp's 16 x D query tile
+  static constexpr int kTileBytes = kPf2Chunk * D * 2;         // K (or V) chunk
+  static constexpr int kStageBytes = 2 * kTileBytes;
+  static constexpr int smem_bytes(int warps) { return warps * kQWarpBytes + kPf2Stages * kStageBytes; }
+};
+
+template <int D>
+__global__ void __launch_bounds__(256, 2)
+paged_attn_prefill_v2_kernel(const bf16* __restrict__ q, int64_t q_stride,
+                             const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache,
+                             const int32_t* __restrict__ block_table, int max_blocks,
+                             const int32_t* __restrict__ cu_q, const int32_t* __restrict__ ctx_lens,
+                             const int32_t* __restrict__ tile_seq, const int32_t* __restrict__ tile_q0,
+                             bf16* __restrict__ out, int Hq, int Hkv, int QT, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using Cfg = Pf2Cfg<D>;
+  constexpr int KS = D / 16;
+  constexpr int NT = D / 8;
+  constexpr int CPR = D / 8;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tile = blockIdx.x, kvh = blockIdx.y;
+  const int G = Hq / Hkv;
+  const int nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = tile_seq[tile], q0 = tile_q0[tile];
+  const int q_begin = cu_q[seq];
+  const int q_len = cu_q[seq + 1] - q_begin;
+  const int ctx = ctx_lens[seq];
+  const int total_len = ctx + q_len;
+  const int g = warp % G, qsub = warp / G;
+  const int head = kvh * G + g;
+  const int tile_tokens = 16 * QT;
+  const int tile_kv_end = min(total_len, ctx + q0 + tile_tokens);
+  const int warp_kv_end = min(total_len, ctx + q0 + qsub * 16 + 16);
+  const int n_chunks = (tile_kv_end + kPf2Chunk - 1) / kPf2Chunk;
+  const int n_pages_seq = (total_len + kPage - 1) / kPage;
+  const int32_t* bt = block_table + (size_t)seq * max_blocks;
+
+  uint8_t* q_smem = smem + warp * Cfg::kQWarpBytes;
+  uint8_t* kv_smem = smem + nwarps * Cfg::kQWarpBytes;
+
+  // ---- this warp's 16 x D query tile -> swizzled smem (cp.async group 0, with chunk 0)
+  for (int ci = lane; ci < 16 * CPR; ci += 32) {
+    const int r = ci / CPR, c = ci % CPR;
+    const int qi = q0 + qsub * 16 + r;
+    const bool valid = qi < q_len;
+    const bf16* src = q + (size_t)(q_begin + (valid ? qi : 0)) * q_stride + (size_t)head * D + c * 8;
+    cp_async_16_zfill(q_smem + swz<D>(r, c), src, valid);
+  }
+
+  auto issue = [&](int c) {
+    uint8_t* st = kv_smem + (c % kPf2Stages) * Cfg::kStageBytes;
+    for (int ci = threadIdx.x; ci < kPf2Chunk * CPR; ci += blockDim.x) {
+      const int r = ci / CPR, cc = ci % CPR;
+      const int tok = c * kPf2Chunk + r;
+      const int page = tok / kPage;
+      const bool valid = page < n_pages_seq;
+      const int blk = valid ? __ldg(bt + page) : 0;
+      const size_t off = (((size_t)blk * Hkv + kvh) * kPage + (tok % kPage)) * D + cc * 8;
+      cp_async_16_zfill(st + swz<D>(r, cc), k_cache + off, valid);
+      cp_async_16_zfill(st + Cfg::kTileBytes + swz<D>(r, cc), v_cache + off, valid);
+    }
+  };
+
+  const int r0 = lane >> 2, r1 = r0 + 8, cb = 2 * (lane & 3);
+  const int qi0 = q0 + qsub * 16 + r0, qi1 = q0 + qsub * 16 + r1;
+  const int qpos0 = ctx + qi0, qpos1 = ctx + qi1;
+  float o[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+#pragma unroll
+  for (int c = 0; c < kPf2Stages - 1; ++c) {
+    if (c < n_chunks) issue(c);
+    cp_async_commit();
+  }
+  const uint32_t q_base = smem_u32(q_smem);
+  const int mi = lane >> 3, rr = lane & 7;
+  const int q_row = rr + (mi & 1) * 8;          // A-fragment row supplied by this lane
+
+  for (int c = 0; c < n_chunks; ++c) {
+    cp_async_wait<kPf2Stages - 2>();
+    __syncthreads();                           // chunk c landed; everyone is done with chunk c-1
+    if (c + kPf2Stages - 1 < n_chunks) issue(c + kPf2Stages - 1);
+    cp_async_commit();
+    if (c * kPf2Chunk >= warp_kv_end) continue;  // fully masked for this warp (warp-uniform)
+
+    const uint32_t k_base = smem_u32(kv_smem + (c % kPf2Stages) * Cfg::kStageBytes);
+    const uint32_t v_base = k_base + Cfg::kTileBytes;
+    float s[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t qf[4];
+      ldsm_x4(q_base + swz<D>(q_row, 2 * ks + (mi >> 1)), qf[0], qf[1], qf[2], qf[3]);
+#pragma unroll
+      for (int tp = 0; tp < 2; ++tp) {
+        const int tok = tp * 16 + rr + (mi >> 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(k_base + swz<D>(tok, 2 * ks + (mi & 1)), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * tp], qf, b0, b1);
+        mma_bf16_16816(s[2 * tp + 1], qf, b2, b3);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kv = c * kPf2Chunk + t * 8 + cb + (e & 1);
+        const int qp = e < 2 ? qpos0 : qpos1;
+        const float v = kv <= qp ? s[t][e] * scale_log2 : -INFINITY;
+        s[t][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float base0 = mn0 == -INFINITY ? 0.f : mn0, base1 = mn1 == -INFINITY ? 0.f : mn1;
+    const float a0 = exp2f(m0 - base0), a1 = exp2f(m1 - base1);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      s[t][0] = exp2f(s[t][0] - base0); s[t][1] = exp2f(s[t][1] - base0);
+      s[t][2] = exp2f(s[t][2] - base1); s[t][3] = exp2f(s[t][3] - base1);
+      rs0 += s[t][0] + s[t][1];
+      rs1 += s[t][2] + s[t][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { o[t][0] *= a0; o[t][1] *= a0; o[t][2] *= a1; o[t][3] *= a1; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t pa[4] = {pack_bf16(s[2 * j][0], s[2 * j][1]), pack_bf16(s[2 * j][2], s[2 * j][3]),
+                              pack_bf16(s[2 * j + 1][0], s[2 * j + 1][1]),
+                              pack_bf16(s[2 * j + 1][2], s[2 * j + 1][3])};
+      const int tok = j * 16 + rr + (mi & 1) * 8;
+#pragma unroll
+      for (int cc = 0; cc < NT; cc += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(v_base + swz<D>(tok, cc + (mi >> 1)), b0, b1, b2, b3);
+        mma_bf16_16816(o[cc], pa, b0, b1);
+        mma_bf16_16816(o[cc + 1], pa, b2, b3);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  const size_t orow = (size_t)Hq * D;
+  if (qi0 < q_len) {
+    bf16* op = out + (size_t)(q_begin + qi0) * orow + (size_t)head * D + cb;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      *reinterpret_cast<uint32_t*>(op + t * 8) = pack_bf16(o[t][0] * i0, o[t][1] * i0);
+  }
+  if (qi1 < q_len) {
+    bf16* op = out + (size_t)(q_begin + qi1) * orow + (size_t)head * D + cb;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      *reinterpret_cast<uint32_t*>(op + t * 8) = pack_bf16(o[t][2] * i1, o[t][3] * i1);
+  }
+}
+
 template <typename K>
 static int set_smem_attr(K kernel, int bytes, const char* what) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -579,7 +765,24 @@ extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, const vo
   const int G = Hq / Hkv, QT = tile / 16;
   dim3 grid(num_tiles, Hkv);
   int rc;
-  if (D == 128) {
+  static int use_v2 = -1;
+  if (use_v2 < 0) {
+    const char* e = getenv("B200_ATTN_PREFILL_V1");
+    use_v2 = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (D == 128 && use_v2) {
+    const int warps = G * QT;
+    const int smem_bytes = Pf2Cfg<128>::smem_bytes(warps);
+    static bool once2 = false;
+    if (!once2) {
+      rc = set_smem_attr(paged_attn_prefill_v2_kernel<128>, Pf2Cfg<128>::smem_bytes(8), "attn_prefill_v2");
+      if (rc) return rc;
+      once2 = true;
+    }
+    (void)launch_pdl(paged_attn_prefill_v2_kernel<128>, dim3(grid), dim3(32 * warps), (size_t)smem_bytes, s, 1,
+                     (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
+                     max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, (bf16*)out, Hq, Hkv, QT, scale_log2);
+  } else if (D == 128) {
     static bool once = false;
     if (!once) {
       rc = set_smem_attr(paged_attn_prefill_kernel<128>, PfCfg<128>::kSmemBytes, "attn_prefill");

@@ -243,14 +243,17 @@ def attn_prefill_tile(Hq, Hkv) -> int:
     return t
 
 
-def build_prefill_tiles(q_lens: Sequence[int], tile: int):
-    """Host-side tile list for b200_paged_attn_prefill: (tile_seq, tile_q0) int32 lists."""
-    seqs, q0s = [], []
+def build_prefill_tiles(q_lens: Sequence[int], tile: int, ctx_lens: Optional[Sequence[int]] = None):
+    """Host-side tile list for b200_paged_attn_prefill: (tile_seq, tile_q0) int32 lists, ordered
+    heaviest first (a causal tile's work grows with its last key position), so the long tiles do
+    not end up alone in the last wave."""
+    tiles = []
     for s, n in enumerate(q_lens):
+        c = 0 if ctx_lens is None else int(ctx_lens[s])
         for q0 in range(0, n, tile):
-            seqs.append(s)
-            q0s.append(q0)
-    return seqs, q0s
+            tiles.append((c + q0 + tile, s, q0))
+    tiles.sort(key=lambda t: -t[0])
+    return [t[1] for t in tiles], [t[2] for t in tiles]
 
 
 def paged_attn_prefill(q, q_stride, k_cache, v_cache, block_table, cu_q, ctx_lens, tile_seq, tile_q0,

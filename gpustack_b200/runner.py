@@ -318,7 +318,7 @@ class ModelRunner:
         o_cu = 3 * _align(T)
         o_ctx = o_cu + _align(S + 1)
         o_rows = o_ctx + _align(S)
-        tile_seq, tile_q0 = ops.build_prefill_tiles(lens, self.prefill_tile)
+        tile_seq, tile_q0 = ops.build_prefill_tiles(lens, self.prefill_tile, starts)
         nt = len(tile_seq)
         o_ts = o_rows + _align(S)
         o_tq = o_ts + _align(nt)
