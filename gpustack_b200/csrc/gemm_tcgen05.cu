@@ -566,13 +566,17 @@ static int pow2_cover(int M) {
   return b;
 }
 
-// Activation-tile width for a given split count.
+// Activation-tile width for a given split count: start from the smallest width covering M and
+// cut it into 2 or 4 m-tiles while that still fits one wave of CTAs (few weight tiles = small N,
+// e.g. tensor-parallel shards: the weights are re-read from L2, not from HBM).
 static int plan_block_x(int M, int N, int splits) {
   if (M > 256) return 256;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int base = pow2_cover(M);
   const int units = ((N + kBlockW - 1) / kBlockW) * splits;
-  if (base >= 64 && units * 2 <= sms + sms / 12) return base / 2;  // two m-tiles fill the wave
+  const int budget = sms + sms / 12;
+  if (base >= 128 && units * 4 <= budget) return base / 4;
+  if (base >= 64 && units * 2 <= budget) return base / 2;
   return base;
 }
 

@@ -144,7 +144,7 @@ class ModelRunner:
         if self.tp > 1:
             ar = self.oneshot
             # one-shot moves (tp-1) x the message over NVLink: right for decode-sized messages only
-            if ar is not None and T <= ar.max_tokens and T * self.H * 2 * (self.tp - 1) <= (4 << 20):
+            if ar is not None and T <= ar.max_tokens and T * self.H * 2 * (self.tp - 1) <= (8 << 20):
                 # GEMM writes its partial into a peer-mapped staging buffer; ONE kernel then pulls
                 # every rank's partial over NVLink, sums, adds the residual and normalises.
                 which = self._ar_toggle
