@@ -25,7 +25,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // stored) and then rotated -- the split-K reduction costs no extra pass.
 template <bool PARTIALS>
 __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, int splits, size_t plane,
-                                      size_t off, float (&f)[8]) {
+                                      size_t off, float (&f)[8], const bf16* bias = nullptr, int col = 0) {
   if constexpr (!PARTIALS) {
     unpack8(ld_v4(qkv + off), f);
     return;
@@ -38,6 +38,12 @@ __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, in
     f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
     f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
   }
+  if (bias != nullptr) {  // QKV bias (Qwen2): added in fp32, the sum is rounded once
+    float bf[8];
+    unpack8(ld_v4(bias + col), bf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += bf[j];
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j]);
 }
@@ -45,7 +51,7 @@ __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, in
 template <bool PARTIALS>
 __global__ void __launch_bounds__(256)
 rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials, int splits, int T,
-                     const int32_t* __restrict__ positions,
+                     const bf16* __restrict__ bias, const int32_t* __restrict__ positions,
                      const bf16* __restrict__ cos_sin, bf16* __restrict__ k_cache,
                      bf16* __restrict__ v_cache, const int32_t* __restrict__ slot_mapping, int Hq,
                      int Hkv, int D, int block_size) {
@@ -71,8 +77,8 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials,
       bf16* p1 = qkv + row + (size_t)head * D + vi * 8;
       bf16* p2 = p1 + half;
       float x1[8], x2[8], c[8], s[8], o1[8], o2[8];
-      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p1 - qkv), x1);
-      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p2 - qkv), x2);
+      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p1 - qkv), x1, bias, head * D + vi * 8);
+      load8<PARTIALS>(qkv, partials, splits, plane, (size_t)(p2 - qkv), x2, bias, head * D + half + vi * 8);
       unpack8(ld_v4(cs + vi * 8), c);
       unpack8(ld_v4(cs + half + vi * 8), s);
 #pragma unroll
@@ -99,7 +105,7 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials,
         st_v4(dst, ld_v4(qkv + voff));
       } else {
         float vf[8];
-        load8<true>(qkv, partials, splits, plane, voff, vf);
+        load8<true>(qkv, partials, splits, plane, voff, vf, bias, (Hq + Hkv + vh) * D + vi * 8);
         const uint4 vv = pack8(vf);
         if (slot >= 0) st_v4(dst, vv);
         st_v4(qkv + voff, vv);
@@ -112,7 +118,7 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const float* __restrict__ partials,
 
 using namespace b200;
 
-static int rope_launch(void* qkv, const float* partials, int splits, const int32_t* positions,
+static int rope_launch(void* qkv, const float* partials, int splits, const void* bias, const int32_t* positions,
                        const void* cos_sin, void* k_cache, void* v_cache, const int32_t* slot_mapping,
                        int T, int Hq, int Hkv, int D, int block_size, void* stream, const char* what) {
   B200_REQUIRE(T >= 0 && Hq > 0 && Hkv > 0 && block_size > 0, "%s: bad shape", what);
@@ -120,11 +126,11 @@ static int rope_launch(void* qkv, const float* partials, int splits, const int32
   if (T == 0) return B200_OK;
   if (partials != nullptr)
     (void)launch_pdl(rope_kv_write_kernel<true>, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
-                     partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
+                     partials, splits, T, (const bf16*)bias, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
                      slot_mapping, Hq, Hkv, D, block_size);
   else
     (void)launch_pdl(rope_kv_write_kernel<false>, dim3(T), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)qkv,
-                     partials, splits, T, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
+                     partials, splits, T, (const bf16*)bias, positions, (const bf16*)cos_sin, (bf16*)k_cache, (bf16*)v_cache,
                      slot_mapping, Hq, Hkv, D, block_size);
   return b200_check_launch(what);
 }
@@ -132,15 +138,15 @@ static int rope_launch(void* qkv, const float* partials, int splits, const int32
 extern "C" int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin,
                                   void* k_cache, void* v_cache, const int32_t* slot_mapping, int T,
                                   int Hq, int Hkv, int D, int block_size, void* stream) {
-  return rope_launch(qkv, nullptr, 0, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq, Hkv, D,
+  return rope_launch(qkv, nullptr, 0, nullptr, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq, Hkv, D,
                      block_size, stream, "b200_rope_kv_write");
 }
 
-extern "C" int b200_rope_kv_write_partials(const float* partials, int splits, void* qkv_out,
-                                           const int32_t* positions, const void* cos_sin, void* k_cache,
+extern "C" int b200_rope_kv_write_partials(const float* partials, int splits, const void* qkv_bias,
+                                           void* qkv_out, const int32_t* positions, const void* cos_sin, void* k_cache,
                                            void* v_cache, const int32_t* slot_mapping, int T, int Hq,
                                            int Hkv, int D, int block_size, void* stream) {
   B200_REQUIRE(partials != nullptr && splits >= 1, "rope_kv_write_partials: partials required");
-  return rope_launch(qkv_out, partials, splits, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq,
+  return rope_launch(qkv_out, partials, splits, qkv_bias, positions, cos_sin, k_cache, v_cache, slot_mapping, T, Hq,
                      Hkv, D, block_size, stream, "b200_rope_kv_write_partials");
 }

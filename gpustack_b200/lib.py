@@ -30,7 +30,7 @@ SIGNATURES = {
     "b200_fused_add_rms_norm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "b200_fused_add_rms_norm_partials": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "b200_rope_kv_write": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "b200_rope_kv_write_partials": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_rope_kv_write_partials": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_silu_and_mul": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "b200_embedding": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200_argmax_f32": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _vp]),

@@ -102,13 +102,14 @@ def rope_kv_write(qkv, positions, cos_sin, k_cache, v_cache, slot_mapping, Hq, H
           "rope_kv_write")
 
 
-def rope_kv_write_partials(partials, qkv_out, positions, cos_sin, k_cache, v_cache, slot_mapping, Hq, Hkv, D):
+def rope_kv_write_partials(partials, qkv_out, positions, cos_sin, k_cache, v_cache, slot_mapping, Hq, Hkv, D,
+                           bias=None):
     """partials [S,T,(Hq+2Hkv)*D] fp32 (split-K QKV GEMM) -> rotated bf16 qkv_out + cache scatter."""
     _req(partials, torch.float32, "partials"); _req(qkv_out, torch.bfloat16, "qkv_out")
     S, T, W = partials.shape
     if W != (Hq + 2 * Hkv) * D or qkv_out.shape[1] != W:
         raise B200Error("rope_kv_write_partials: qkv width mismatch")
-    check(load().b200_rope_kv_write_partials(_p(partials), S, _p(qkv_out), _p(positions), _p(cos_sin), _p(k_cache),
+    check(load().b200_rope_kv_write_partials(_p(partials), S, _p(bias), _p(qkv_out), _p(positions), _p(cos_sin), _p(k_cache),
                                              _p(v_cache), _p(slot_mapping), T, Hq, Hkv, D, k_cache.shape[2],
                                              _stream()), "rope_kv_write_partials")
 

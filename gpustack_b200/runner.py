@@ -90,7 +90,9 @@ class ModelRunner:
         self.logits = e(self.max_seqs, self.v_local, dt=torch.float32)
         self.out_ids = torch.zeros(self.max_seqs, dtype=torch.int32, device=dev)
         self.out_vals = torch.zeros(self.max_seqs, dtype=torch.float32, device=dev)
-        self.partials = e(8 * min(_SPLITK_MAX_M, T) * max(H, self.qkv_width), dt=torch.float32)   # flat: [splits, T, W]
+        has_bias = self.w.layers[0].qkv_bias is not None
+        n_part = max(8 * min(_SPLITK_MAX_M, T) * max(H, self.qkv_width), T * self.qkv_width if has_bias else 0)
+        self.partials = e(n_part, dt=torch.float32)   # flat: [splits, T, W]
         self.cos_sin = self._cos_sin_cache().to(dev)
         # one int32 staging area for all step inputs (host pinned + device mirror)
         n_tiles_max = T // self.prefill_tile + self.max_seqs + 1
@@ -178,17 +180,16 @@ class ModelRunner:
         ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
         self.stats["kernel_launches"] += 2   # embedding (by the caller) + this norm
         for l, lw in enumerate(w.layers):
-            qs = ops.gemm_suggest_splits(T, lw.qkv.shape[0], lw.qkv.shape[1]) \
-                if (T <= _SPLITK_MAX_M and lw.qkv_bias is None) else 1
-            if qs > 1:   # split-K partials are reduced inside the RoPE + KV-write kernel
+            qs = ops.gemm_suggest_splits(T, lw.qkv.shape[0], lw.qkv.shape[1]) if T <= _SPLITK_MAX_M else 1
+            if qs > 1 or lw.qkv_bias is not None:
+                # fp32 (split-K) partials are reduced -- and the Qwen2 QKV bias added, one rounding --
+                # inside the RoPE + KV-write kernel
                 parts = self.partials[:qs * T * self.qkv_width].view(qs, T, self.qkv_width)
-                ops.gemm(self.xn[:T], lw.qkv, out=parts, splits=qs)
+                ops.gemm(self.xn[:T], lw.qkv, out=parts if qs > 1 else parts[0], out_dtype=torch.float32, splits=qs)
                 ops.rope_kv_write_partials(parts, self.qkv[:T], pos, self.cos_sin, self.k_cache[l],
-                                           self.v_cache[l], slots, self.Hq, self.Hkv, self.D)
+                                           self.v_cache[l], slots, self.Hq, self.Hkv, self.D, bias=lw.qkv_bias)
             else:
                 ops.gemm(self.xn[:T], lw.qkv, out=self.qkv[:T])
-                if lw.qkv_bias is not None:
-                    self.qkv[:T].add_(lw.qkv_bias)
                 ops.rope_kv_write(self.qkv[:T], pos, self.cos_sin, self.k_cache[l], self.v_cache[l], slots,
                                   self.Hq, self.Hkv, self.D)
             attn_fn(l)

@@ -62,9 +62,10 @@ int b200_rope_kv_write(void* qkv, const int32_t* positions, const void* cos_sin,
                        int block_size, void* stream);
 
 /* Same, with the QKV projection arriving as `splits` fp32 split-K partial sums
- * [splits][T][(Hq+2Hkv)*D]: they are summed and rounded to bf16 (what the un-split GEMM would have
- * stored), rotated, written to qkv_out (bf16, same layout) and scattered into the cache. */
-int b200_rope_kv_write_partials(const float* partials, int splits, void* qkv_out,
+ * [splits][T][(Hq+2Hkv)*D]: they are summed, the optional QKV bias [(Hq+2Hkv)*D] bf16 (Qwen2) is added
+ * in fp32, the result is rounded to bf16 (what the un-split GEMM would have stored), rotated,
+ * written to qkv_out (bf16, same layout) and scattered into the cache. */
+int b200_rope_kv_write_partials(const float* partials, int splits, const void* qkv_bias, void* qkv_out,
                                 const int32_t* positions, const void* cos_sin, void* k_cache,
                                 void* v_cache, const int32_t* slot_mapping, int T, int Hq, int Hkv,
                                 int D, int block_size, void* stream);

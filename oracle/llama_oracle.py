@@ -77,9 +77,13 @@ def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.silu(x[..., :d]) * x[..., d:]
 
 
-def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """$VLLM/model_executor/layers/utils.py:92-98 -- F.linear, fp32 accumulation, bf16 result."""
-    return (x.to(torch.float32) @ w.to(torch.float32).t()).to(x.dtype)
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """$VLLM/model_executor/layers/utils.py:92-98 -- F.linear: fp32 accumulation (+ bias in fp32),
+    one rounding to bf16."""
+    y = x.to(torch.float32) @ w.to(torch.float32).t()
+    if b is not None:
+        y = y + b.to(torch.float32)
+    return y.to(x.dtype)
 
 
 def attention_ref(q, k, v, scale: float, q_pos: torch.Tensor) -> torch.Tensor:
@@ -121,6 +125,7 @@ class LlamaConfig:
     rope_theta: float = 500000.0
     max_position_embeddings: int = 8192
     tie_word_embeddings: bool = False
+    attention_bias: bool = False      # Qwen2: bias on q/k/v projections
 
     @property
     def q_size(self):
@@ -139,7 +144,11 @@ TINY128 = LlamaConfig(vocab_size=640, hidden_size=512, intermediate_size=1024, n
 QWEN2_05B_SHAPE = LlamaConfig(vocab_size=151936, hidden_size=896, intermediate_size=4864,
                               num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2,
                               head_dim=64, rms_norm_eps=1e-6, rope_theta=1e6,
-                              max_position_embeddings=32768, tie_word_embeddings=True)
+                              max_position_embeddings=32768, tie_word_embeddings=True, attention_bias=True)
+TINY_QWEN2 = LlamaConfig(vocab_size=1000, hidden_size=896, intermediate_size=1024, num_hidden_layers=2,
+                         num_attention_heads=14, num_key_value_heads=2, head_dim=64, rms_norm_eps=1e-6,
+                         rope_theta=1e6, max_position_embeddings=512, tie_word_embeddings=True,
+                         attention_bias=True)
 LLAMA3_8B = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
                         num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, head_dim=128)
 
@@ -161,6 +170,10 @@ def init_weights(cfg: LlamaConfig, seed: int = 0, std: float = 0.02, device="cpu
         w[p + "self_attn.q_proj.weight"] = rnd(cfg.q_size, H)
         w[p + "self_attn.k_proj.weight"] = rnd(cfg.kv_size, H)
         w[p + "self_attn.v_proj.weight"] = rnd(cfg.kv_size, H)
+        if cfg.attention_bias:
+            w[p + "self_attn.q_proj.bias"] = rnd(cfg.q_size, s=0.5)
+            w[p + "self_attn.k_proj.bias"] = rnd(cfg.kv_size, s=0.5)
+            w[p + "self_attn.v_proj.bias"] = rnd(cfg.kv_size, s=0.5)
         w[p + "self_attn.o_proj.weight"] = rnd(H, cfg.q_size)
         w[p + "post_attention_layernorm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
         w[p + "mlp.gate_proj.weight"] = rnd(I, H)
@@ -229,9 +242,13 @@ class OracleLlama:
 
     def _lin(self, x: torch.Tensor, name: str) -> torch.Tensor:
         wf = self.wf.get(name)
+        b = self.w.get(name.replace(".weight", ".bias"))
         if wf is None:
-            return linear(x, self.w[name])
-        return (x.to(torch.float32) @ wf.t()).to(x.dtype)
+            return linear(x, self.w[name], b)
+        y = x.to(torch.float32) @ wf.t()
+        if b is not None:
+            y = y + b.to(torch.float32)
+        return y.to(x.dtype)
 
     def generate(self, seq_id: int, prompt: Sequence[int], max_new_tokens: int) -> List[int]:
         """greedy decode ($VLLM/v1/sample/sampler.py: argmax over fp32 logits, lowest index wins)."""

@@ -85,6 +85,35 @@ def tiny_llama_from_hf():
     print("wrote tiny_llama_hf.pt")
 
 
+def tiny_qwen2_from_hf():
+    """Qwen2 family (BASELINE.json configs[0]): q/k/v bias + tied embeddings, GQA group of 7."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    cfg = O.TINY_QWEN2
+    weights = O.init_weights(cfg, seed=7)
+    hf_cfg = Qwen2Config(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        num_key_value_heads=cfg.num_key_value_heads, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+        max_position_embeddings=cfg.max_position_embeddings, tie_word_embeddings=True, use_sliding_window=False,
+        attn_implementation="eager")
+    g = torch.Generator().manual_seed(43)
+    prompt = torch.randint(3, cfg.vocab_size, (1, 19), generator=g)
+    res = {"prompt": prompt[0].tolist()}
+    for dt, key in ((torch.float32, "fp32"), (BF, "bf16")):
+        model = Qwen2ForCausalLM(hf_cfg).to(dt).eval()
+        sd = {k: v.to(dt) for k, v in weights.items()}
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            res[f"logits_{key}"] = model(prompt).logits[0].float()[-4:].clone()
+            gen = model.generate(prompt, max_new_tokens=10, do_sample=False, pad_token_id=0)
+        res[f"greedy_{key}"] = gen[0, prompt.shape[1]:].tolist()
+    torch.save(res, OUT / "tiny_qwen2_hf.pt")
+    print("wrote tiny_qwen2_hf.pt")
+
+
 if __name__ == "__main__":
     ops_from_vllm()
     tiny_llama_from_hf()
+    tiny_qwen2_from_hf()

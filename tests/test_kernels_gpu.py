@@ -138,6 +138,14 @@ def test_rope_kv_write_from_splitk_partials(ops, out_dir):
     out = torch.empty(T, W, dtype=BF, device="cuda")
     ops.rope_kv_write_partials(parts.cuda(), out, pos.cuda(), cache.cuda(), kc2, vc2, slots.cuda(), Hq, Hkv, D)
     assert torch.equal(out, ref_qkv) and torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    # with a QKV bias (Qwen2): added in fp32 before the single bf16 rounding
+    bias = (torch.randn(W, generator=g) * 0.5).to(BF)
+    ref_b = (acc + bias.float()).to(BF).cuda()
+    kc3 = torch.zeros_like(kc1); vc3 = torch.zeros_like(kc1); kc4 = torch.zeros_like(kc1); vc4 = torch.zeros_like(kc1)
+    ops.rope_kv_write(ref_b, pos.cuda(), cache.cuda(), kc3, vc3, slots.cuda(), Hq, Hkv, D)
+    ops.rope_kv_write_partials(parts.cuda(), out, pos.cuda(), cache.cuda(), kc4, vc4, slots.cuda(), Hq, Hkv, D,
+                               bias=bias.cuda())
+    assert torch.equal(out, ref_b) and torch.equal(kc3, kc4) and torch.equal(vc3, vc4)
 
 
 @pytest.mark.parametrize("T,I", [(1, 14336), (65, 14336), (9, 4864), (300, 1024)])

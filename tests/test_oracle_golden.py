@@ -81,3 +81,17 @@ def test_paged_gather_and_attention_shapes():
     # causality: the first query must ignore keys 38, 39
     o2 = O.attention_ref(q[:1], kv[:38], kv[:38], 0.125, torch.tensor([37]))
     assert torch.equal(o[:1], o2)
+
+
+def test_qwen2_family_against_hf():
+    """q/k/v bias, tied embeddings, GQA group of 7 (the Qwen2-0.5B family of BASELINE.json configs[0])."""
+    g = torch.load(GOLD / "tiny_qwen2_hf.pt", weights_only=False)
+    model = O.OracleLlama(O.TINY_QWEN2, O.init_weights(O.TINY_QWEN2, seed=7))
+    logits = model.forward(0, g["prompt"])[-4:]
+    scale = float(g["logits_fp32"].abs().max())
+    assert float((logits - g["logits_fp32"]).abs().max()) <= 2e-2 * scale
+    model.reset()
+    mine = model.generate(0, g["prompt"], 10)
+    agree = [a == b for a, b in zip(g["greedy_fp32"], g["greedy_bf16"])]
+    n_stable = agree.index(False) if False in agree else len(agree)
+    assert mine[:n_stable] == g["greedy_fp32"][:n_stable]
