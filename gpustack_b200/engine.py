@@ -24,6 +24,89 @@ from .weights import ModelWeights, load_safetensors_dir, random_state_dict, shar
 _KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED = 0, 1, 2, 3, 4
 
 
+class ShmStepChannel:
+    """Single-writer (rank 0) / multi-reader step channel in POSIX shared memory: the per-step
+    scheduler output (a few KB to ~2 MB of int32) reaches the other ranks of the node in ~10 us
+    instead of two gloo broadcasts (~250 us).  Counterpart of the reference engine's shared-memory
+    MessageQueue ($VLLM/distributed/device_communicators/shm_broadcast.py).
+    Layout: [0:8) sequence number (written LAST), [8:16) payload words, [16:80) 8 x int64 header,
+    [128 + 8 r) ack of rank r, [4096: ...) int32 payload.  x86 store ordering + the copy-out before
+    the ack make a fence-free protocol sufficient here."""
+
+    PAYLOAD_OFF = 4096
+
+    def __init__(self, rank: int, world: int, dist, cpu_group, capacity_words: int = 1 << 20):
+        from multiprocessing import shared_memory
+
+        self.rank, self.world = rank, world
+        names = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.PAYLOAD_OFF + capacity_words * 4)
+            self.shm.buf[: self.PAYLOAD_OFF] = bytes(self.PAYLOAD_OFF)
+            names[0] = self.shm.name
+        dist.broadcast_object_list(names, src=0, group=cpu_group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=names[0])
+            try:   # only the creator may unlink; keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
+        self.cap = capacity_words
+        self.seq = np.ndarray((1,), dtype=np.uint64, buffer=self.shm.buf, offset=0)
+        self.nwords = np.ndarray((1,), dtype=np.int64, buffer=self.shm.buf, offset=8)
+        self.header = np.ndarray((8,), dtype=np.int64, buffer=self.shm.buf, offset=16)
+        self.acks = np.ndarray((world,), dtype=np.uint64, buffer=self.shm.buf, offset=128)
+        self.payload = np.ndarray((capacity_words,), dtype=np.int32, buffer=self.shm.buf, offset=self.PAYLOAD_OFF)
+        self.last = 0
+        dist.barrier(group=cpu_group)
+
+    @staticmethod
+    def _spin(cond) -> None:
+        n = 0
+        while not cond():
+            n += 1
+            if n > 20000:
+                time.sleep(0.0002 if n < 200000 else 0.002)   # idle engine: stop burning a core
+            elif (n & 63) == 0:
+                time.sleep(0)
+
+    def send(self, header: List[int], payload: Optional[np.ndarray]) -> None:
+        cur = self.last
+        self._spin(lambda: all(int(self.acks[r]) == cur for r in range(1, self.world)))
+        n = 0 if payload is None else len(payload)
+        if n > self.cap:
+            raise B200Error(f"step payload of {n} words exceeds the shared-memory channel ({self.cap})")
+        if n:
+            self.payload[:n] = payload
+        self.header[:] = 0
+        self.header[: len(header)] = header
+        self.nwords[0] = n
+        self.last = cur + 1
+        self.seq[0] = self.last            # publish
+
+    def recv(self):
+        nxt = self.last + 1
+        self._spin(lambda: int(self.seq[0]) >= nxt)
+        n = int(self.nwords[0])
+        header = self.header.tolist()
+        payload = self.payload[:n].copy() if n else None
+        self.last = nxt
+        self.acks[self.rank] = nxt         # rank 0 may now overwrite the buffer
+        return header, payload
+
+    def close(self) -> None:
+        try:
+            for a in ("seq", "nwords", "header", "acks", "payload"):
+                setattr(self, a, None)
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class TPContext:
     """torch.distributed plumbing for one tensor-parallel group (one process per GPU)."""
 
@@ -33,7 +116,17 @@ class TPContext:
         self.rank, self.world, self.device = rank, world, device
         self.dist = dist
         self.nccl = dist.group.WORLD
-        self.cpu = dist.new_group(backend="gloo")   # step metadata travels over gloo
+        self.cpu = dist.new_group(backend="gloo")   # bootstrap / barriers; fallback step channel
+        self.shm: Optional[ShmStepChannel] = None
+        if os.environ.get("B200_TP_STEP_CHANNEL", "shm") == "shm":
+            try:
+                self.shm = ShmStepChannel(rank, world, dist, self.cpu)
+            except Exception:  # noqa: BLE001  (no /dev/shm, ...): gloo still works
+                self.shm = None
+            ok = torch.tensor([1 if self.shm is not None else 0])
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.cpu)
+            if int(ok[0]) == 0:
+                self.shm = None
 
     @staticmethod
     def from_env() -> Optional["TPContext"]:
@@ -51,6 +144,11 @@ class TPContext:
 
     def bcast_step(self, header: List[int], payload: Optional[np.ndarray]):
         """rank 0 sends (header, int32 payload); the other ranks receive them."""
+        if self.shm is not None:
+            if self.rank == 0:
+                self.shm.send(header, None if payload is None else np.ascontiguousarray(payload, dtype=np.int32))
+                return header + [0] * (8 - len(header)), payload
+            return self.shm.recv()
         h = torch.zeros(8, dtype=torch.int64)
         if self.rank == 0:
             h[:len(header)] = torch.tensor(header, dtype=torch.int64)
@@ -196,6 +294,10 @@ class LLMEngine:
     def shutdown(self) -> None:
         if self.tp and self.tp.rank == 0:
             self.tp.bcast_step([_KIND_STOP], None)
+            if self.tp.shm is not None:
+                time.sleep(0.05)            # let the workers read the STOP before the segment goes
+                self.tp.shm.close()
+                self.tp.shm = None
 
     # ------------------------------------------------------------------ timing helpers (bench.py)
     def sync_mark(self) -> float:
@@ -251,6 +353,9 @@ class TPWorker:
             h, p = tp.bcast_step([0], None)
             kind = h[0]
             if kind == _KIND_STOP:
+                if tp.shm is not None:
+                    tp.shm.close()
+                    tp.shm = None
                 return
             if kind == _KIND_SYNC:
                 self.engine._do_sync_mark()

@@ -82,3 +82,46 @@ def test_step_broadcast_roundtrip():
     assert calls[0] == ("decode", 3, [7, 8, 9], [20, 33, 5],
                         [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]])
     assert calls[1] == ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False])
+
+
+def _stress(rank, port, q, channel):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2",
+                      B200_TP_STEP_CHANNEL=channel)
+    import torch
+    import torch.distributed as dist
+
+    from gpustack_b200 import engine as E
+
+    dist.init_process_group(backend="gloo", rank=rank, world_size=2)
+    tp = E.TPContext(rank, 2, torch.device("cpu"))
+    assert (tp.shm is not None) == (channel == "shm")
+    rs = np.random.RandomState(0)
+    ok, n_steps = True, 1500
+    for i in range(n_steps):
+        n = int(rs.randint(1, 5000))
+        payload = rs.randint(0, 1 << 30, size=n).astype(np.int32)
+        if rank == 0:
+            tp.bcast_step([E._KIND_DECODE, i, n], payload)
+        else:
+            h, p = tp.bcast_step([0], None)
+            ok = ok and h[0] == E._KIND_DECODE and h[1] == i and h[2] == n and np.array_equal(p, payload)
+    if tp.shm is not None:
+        dist.barrier(group=tp.cpu)
+        tp.shm.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("channel", ["shm", "gloo"])
+def test_step_channel_stress(channel):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _port()
+    ps = [ctx.Process(target=_stress, args=(r, port, q, channel)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True}
