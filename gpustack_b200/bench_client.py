@@ -22,7 +22,9 @@ import aiohttp
 import numpy as np
 
 
-async def one_request(session, url, model, prompt_ids, max_tokens, chat: bool, results, sem):
+async def one_request(session, url, model, prompt_ids, max_tokens, chat: bool, results, sem, delay: float = 0.0):
+    if delay > 0:
+        await asyncio.sleep(delay)
     async with sem:
         if chat:
             payload = {"model": model, "messages": [{"role": "user", "content": prompt_ids}],
@@ -34,7 +36,7 @@ async def one_request(session, url, model, prompt_ids, max_tokens, chat: bool, r
                        "stream_options": {"include_usage": True}, "ignore_eos": True, "temperature": 0}
             path = "/v1/completions"
         t0 = time.time()
-        first, usage = None, None
+        first, usage, last, n_chunks = None, None, None, 0
         try:
             async with session.post(url + path, json=payload) as resp:
                 if resp.status != 200:
@@ -43,8 +45,11 @@ async def one_request(session, url, model, prompt_ids, max_tokens, chat: bool, r
                 async for raw in resp.content:
                     if not raw.startswith(b"data:"):
                         continue
+                    now = time.time()
                     if first is None:
-                        first = time.time()
+                        first = now
+                    last = now
+                    n_chunks += 1
                     data = raw[5:].strip()
                     if data == b"[DONE]":
                         break
@@ -58,9 +63,15 @@ async def one_request(session, url, model, prompt_ids, max_tokens, chat: bool, r
             return
         t1 = time.time()
         results.append((usage, t1 - t0, (first - t0) * 1000.0 if first else None))
+        if usage and first and usage.get("completion_tokens", 0) > 1:
+            results[-1] = results[-1] + ((t1 - first) * 1000.0 / (usage["completion_tokens"] - 1),)
 
 
-async def run(url, model, n, concurrency, input_len, output_len, seed, vocab, chat=False, text_prompts=None):
+async def run(url, model, n, concurrency, input_len, output_len, seed, vocab, chat=False, text_prompts=None,
+              rate: float = 0.0):
+    """rate > 0: constant-rate arrivals (request i starts at i / rate seconds, the guidellm
+    `constant` profile GPUStack's in-product benchmark uses, gpustack/worker/benchmark/runner.py:208-276);
+    rate <= 0: all requests offered at once, bounded by `concurrency`."""
     rng = random.Random(seed)
     sem = asyncio.Semaphore(concurrency)
     results = []
@@ -75,13 +86,15 @@ async def run(url, model, n, concurrency, input_len, output_len, seed, vocab, ch
                 lo = 256 if vocab > 1024 else 3
                 prompts.append([rng.randrange(lo, vocab - lo) for _ in range(input_len)])
         t0 = time.time()
-        await asyncio.gather(*(one_request(session, url, model, p, output_len, chat, results, sem) for p in prompts))
+        await asyncio.gather(*(one_request(session, url, model, p, output_len, chat, results, sem,
+                                           i / rate if rate > 0 else 0.0) for i, p in enumerate(prompts)))
         total = time.time() - t0
     ok = [r for r in results if r is not None and r[0] is not None]
     comp = sum(r[0]["completion_tokens"] for r in ok)
     prm = sum(r[0]["prompt_tokens"] for r in ok)
     ttft = [r[2] for r in ok if r[2] is not None]
     lat = [r[1] for r in ok]
+    tpot = [r[3] for r in ok if len(r) > 3]
     pct = lambda a, q: float(np.percentile(a, q)) if a else None
     return {
         "requests": n, "successful": len(ok), "concurrency": concurrency, "total_time_s": total,
@@ -89,6 +102,7 @@ async def run(url, model, n, concurrency, input_len, output_len, seed, vocab, ch
         "completion_tokens": comp, "prompt_tokens": prm, "mean_prompt_tokens": prm / max(1, len(ok)),
         "ttft_ms_p50": pct(ttft, 50), "ttft_ms_p95": pct(ttft, 95), "ttft_ms_p99": pct(ttft, 99),
         "latency_s_p50": pct(lat, 50), "latency_s_p99": pct(lat, 99),
+        "tpot_ms_p50": pct(tpot, 50), "tpot_ms_p99": pct(tpot, 99), "request_rate": rate,
     }
 
 
@@ -103,10 +117,11 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--vocab", type=int, default=128256)
     ap.add_argument("--repeat", type=int, default=1, help="run the workload this many times; one JSON line each")
+    ap.add_argument("--rate", type=float, default=0.0, help="constant request rate (req/s); <= 0 = all at once")
     a = ap.parse_args()
     for k in range(a.repeat):
         r = asyncio.run(run(a.url, a.model, a.num_requests, a.concurrency, a.input_len, a.output_len,
-                            a.seed + k, a.vocab))
+                            a.seed + k, a.vocab, rate=a.rate))
         print(json.dumps(r), flush=True)
 
 

@@ -202,3 +202,44 @@ def test_frontend_process_split_streams_over_the_pipe():
         front.join(timeout=10)
         th.join(timeout=10)
     assert not th.is_alive()
+
+
+def test_bench_client_against_the_frontend_process():
+    """The load generator (reference metric definitions: TTFT = first SSE chunk, tok/s = completion
+    tokens / wall) against the real frontend process, offered-at-once and constant-rate modes."""
+    import asyncio
+    import socket
+    import threading
+    import types
+    import urllib.request
+
+    from gpustack_b200.bench_client import run
+    from gpustack_b200.frontend import spawn_frontend
+
+    eng = StubEngine()
+    eng.mcfg = types.SimpleNamespace(vocab_size=600, bos_token_id=1, eos_token_id=2)
+    eng.ecfg = types.SimpleNamespace(max_model_len=512)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    front, core = spawn_frontend(eng, "127.0.0.1", port, "stub-model", None, "error")
+    th = threading.Thread(target=core.run, daemon=True)
+    th.start()
+    try:
+        url = f"http://127.0.0.1:{port}"
+        for _ in range(300):
+            try:
+                if urllib.request.urlopen(url + "/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.1)
+        r = asyncio.run(run(url, "stub-model", 12, 6, 20, 16, 0, 600))
+        assert r["successful"] == 12 and r["completion_tokens"] == 12 * 16 and r["prompt_tokens"] == 12 * 20
+        assert r["ttft_ms_p50"] > 0 and r["output_tok_s"] > 0 and r["tpot_ms_p50"] is not None
+        t0 = time.time()
+        r = asyncio.run(run(url, "stub-model", 6, 6, 10, 8, 0, 600, rate=10.0))
+        assert r["successful"] == 6 and time.time() - t0 >= 0.5      # 6 requests at 10 req/s
+    finally:
+        front.terminate()
+        front.join(timeout=10)
+        th.join(timeout=10)
