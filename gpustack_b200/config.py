@@ -49,7 +49,8 @@ class ModelConfig:
         """bf16 bytes streamed per decode step on one rank (layers + lm_head + final norm)."""
         H, I = self.hidden_size, self.intermediate_size
         per_layer = (self.q_size + 2 * self.kv_size) * H + self.q_size * H + 3 * I * H
-        return 2 * (self.num_hidden_layers * per_layer // tp + self.vocab_size * H // tp + H)
+        norms = (2 * self.num_hidden_layers + 1) * H          # replicated
+        return 2 * (self.num_hidden_layers * per_layer // tp + self.vocab_size * H // tp + norms)
 
     @staticmethod
     def from_dict(d: dict) -> "ModelConfig":

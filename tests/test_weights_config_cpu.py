@@ -1,0 +1,106 @@
+"""Weight sharding, checkpoint round trip and config parsing (CPU): the tensor-parallel shards must
+reassemble to exactly the un-sharded computation (QKV/gate_up column-parallel,
+O/down row-parallel + sum, vocab-parallel lm_head), and an HF-format directory written by
+save_checkpoint must load back bit-identically."""
+import json
+
+import pytest
+import torch
+
+from gpustack_b200.config import EngineConfig, ModelConfig, llama3_8b, tiny_llama
+from gpustack_b200.weights import (check_tp, load_safetensors_dir, random_state_dict, save_checkpoint,
+                                   shard_state_dict)
+
+
+def _cfg(bias=False, tie=False):
+    return ModelConfig(vocab_size=300, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                       num_attention_heads=8, num_key_value_heads=4, head_dim=16, attention_bias=bias,
+                       tie_word_embeddings=tie, architecture="Qwen2ForCausalLM" if bias else "LlamaForCausalLM")
+
+
+@pytest.mark.parametrize("tp", [1, 2, 4])
+def test_shards_reassemble_to_the_full_projection(tp):
+    cfg = _cfg(bias=True)
+    sd = random_state_dict(cfg, seed=1, device="cpu")
+    x = torch.randn(5, cfg.hidden_size)
+    shards = [shard_state_dict(cfg, lambda k: sd[k], r, tp, "cpu") for r in range(tp)]
+    D, hq, hkv, I = cfg.head_dim, cfg.num_attention_heads // tp, cfg.num_key_value_heads // tp, cfg.intermediate_size // tp
+    p = "model.layers.1."
+    full_q = x @ sd[p + "self_attn.q_proj.weight"].float().t()
+    full_k = x @ sd[p + "self_attn.k_proj.weight"].float().t()
+    full_v = x @ sd[p + "self_attn.v_proj.weight"].float().t()
+    qs, ks, vs, gates, ups = [], [], [], [], []
+    for sh in shards:
+        lw = sh.layers[1]
+        y = x @ lw.qkv.float().t()
+        qs.append(y[:, : hq * D]); ks.append(y[:, hq * D:(hq + hkv) * D]); vs.append(y[:, (hq + hkv) * D:])
+        gu = x @ lw.gate_up.float().t()           # interleaved rows: 2i = gate_i, 2i+1 = up_i
+        gates.append(gu[:, 0::2]); ups.append(gu[:, 1::2])
+        assert lw.qkv_bias.shape[0] == (hq + 2 * hkv) * D
+    assert torch.equal(torch.cat(qs, 1), full_q) and torch.equal(torch.cat(ks, 1), full_k)
+    assert torch.equal(torch.cat(vs, 1), full_v)
+    assert torch.equal(torch.cat(gates, 1), x @ sd[p + "mlp.gate_proj.weight"].float().t())
+    assert torch.equal(torch.cat(ups, 1), x @ sd[p + "mlp.up_proj.weight"].float().t())
+    bias_q = torch.cat([sh.layers[1].qkv_bias[: hq * D] for sh in shards])
+    assert torch.equal(bias_q, sd[p + "self_attn.q_proj.bias"])
+    # row-parallel: partial products sum to the full product
+    a = torch.randn(5, cfg.q_size)
+    parts = sum(a[:, r * hq * D:(r + 1) * hq * D] @ shards[r].layers[1].o.float().t() for r in range(tp))
+    torch.testing.assert_close(parts, a @ sd[p + "self_attn.o_proj.weight"].float().t(), rtol=1e-5, atol=1e-5)
+    h = torch.randn(5, cfg.intermediate_size)
+    parts = sum(h[:, r * I:(r + 1) * I] @ shards[r].layers[1].down.float().t() for r in range(tp))
+    torch.testing.assert_close(parts, h @ sd[p + "mlp.down_proj.weight"].float().t(), rtol=1e-5, atol=1e-5)
+    # vocab-parallel lm_head covers the vocabulary exactly once, in order
+    assert [s.vocab_start for s in shards] == [r * ((300 + tp - 1) // tp) for r in range(tp)]
+    assert shards[-1].vocab_end == 300
+    assert torch.equal(torch.cat([s.lm_head for s in shards]), sd["lm_head.weight"])
+
+
+def test_tied_embeddings_share_storage_on_one_gpu():
+    cfg = _cfg(tie=True)
+    sd = random_state_dict(cfg, seed=2, device="cpu")
+    assert "lm_head.weight" not in sd
+    w = shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu")
+    assert w.lm_head.data_ptr() == w.embed.data_ptr()
+
+
+def test_checkpoint_round_trip(tmp_path):
+    cfg = _cfg()
+    sd = random_state_dict(cfg, seed=3, device="cpu")
+    save_checkpoint(cfg, sd, str(tmp_path / "ckpt"), shard_bytes=200_000)     # forces several shards + index
+    assert (tmp_path / "ckpt" / "model.safetensors.index.json").exists()
+    cfg2 = ModelConfig.from_pretrained(str(tmp_path / "ckpt"))
+    assert cfg2.hidden_size == cfg.hidden_size and cfg2.head_dim == cfg.head_dim and cfg2.num_key_value_heads == 4
+    a = load_safetensors_dir(cfg2, str(tmp_path / "ckpt"), 0, 1, "cpu")
+    b = shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu")
+    for la, lb in zip(a.layers, b.layers):
+        for f in ("qkv", "o", "gate_up", "down", "input_norm", "post_norm"):
+            assert torch.equal(getattr(la, f), getattr(lb, f))
+    assert torch.equal(a.embed, b.embed) and torch.equal(a.lm_head, b.lm_head)
+
+
+def test_tp_divisibility_rule_matches_the_reference_scheduler():
+    with pytest.raises(ValueError):
+        check_tp(llama3_8b(), 16)           # 8 kv heads: TP <= 8
+    with pytest.raises(ValueError):
+        check_tp(llama3_8b(), 3)
+    for t in (1, 2, 4, 8):
+        check_tp(llama3_8b(), t)
+
+
+def test_config_parsing_and_byte_accounting():
+    c = llama3_8b()
+    assert c.weight_bytes(1) == 15_009_849_344 and c.kv_bytes_per_token(1) == 131_072
+    assert c.kv_bytes_per_token(8) == 16_384
+    hf = {"architectures": ["LlamaForCausalLM"], "vocab_size": 100, "hidden_size": 64, "intermediate_size": 128,
+          "num_hidden_layers": 1, "num_attention_heads": 4, "rope_theta": 1e4, "eos_token_id": [7, 9]}
+    m = ModelConfig.from_dict(hf)
+    assert m.head_dim == 16 and m.num_key_value_heads == 4 and m.eos_token_id == 7
+    with pytest.raises(ValueError):
+        ModelConfig.from_dict({**hf, "architectures": ["MixtralForCausalLM"]})
+    with pytest.raises(ValueError):
+        ModelConfig.from_dict({**hf, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+    e = EngineConfig(max_num_seqs=100)
+    b = e.graph_buckets()
+    assert b[0] == 1 and b[-1] == 100 and b == sorted(set(b))
+    assert tiny_llama(128).head_dim == 128
