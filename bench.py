@@ -329,9 +329,15 @@ def run_ours(a):
     gp = timer.get("gemm_prefill", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
     gd = timer.get("gemm_decode", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
     ach = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] else 0.0
-    roofline = {"kernel": "gemm_bf16_tcgen05_kernel<256> (prefill projections)", "bound": "tensor",
-                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "launches": gp["launches"],
+    traffic, traffic_src = None, None
+    tp_ = ROOT / "profiles" / "r1_gemm_prefill_traffic.json"
+    if tp_.exists() and a.model == "llama3-8b" and a.gpus == 1:
+        tj = json.loads(tp_.read_text())     # dram__bytes_read+write per launch from the committed ncu capture
+        traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
+    roofline = {"kernel": "gemm_bf16_tcgen05_2sm_kernel<256,*> (prefill projections: QKV, O, gate_up+SiLU, down)",
+                "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": gp["bytes"] / max(1, gp["launches"]), "launches": gp["launches"],
                 "avg_launch_ms": gp["ms"] / max(1, gp["launches"]), "share_of_step": gp["ms"] / ev_ms,
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16)"}
     # ---- decode phase as a whole against the HBM roofline (weights + KV streamed per step)
