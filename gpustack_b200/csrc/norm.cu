@@ -6,6 +6,8 @@
 #include "runtime.h"
 #include "../../include/b200.h"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int kMaxVecPerThread = 4;  // H <= 8 * 4 * 1024
@@ -103,11 +105,15 @@ rms_norm_kernel(const bf16* __restrict__ x, const float* __restrict__ partials, 
 }
 
 static int norm_threads(int H) {
+  static int vec_per_thread = -1;   // B200_NORM_VPT: 16-byte vectors per thread (tuning knob)
+  if (vec_per_thread < 0) {
+    const char* e = getenv("B200_NORM_VPT");
+    vec_per_thread = (e && atoi(e) >= 1 && atoi(e) <= kMaxVecPerThread) ? atoi(e) : 2;  // measured: 2 -> 5.9 TB/s (1: 4.4, 4: 5.5)
+  }
   int nvec = H / 8;
-  int t = (nvec + 31) / 32 * 32;
-  if (t > 1024) t = 1024;
-  // prefer >= 2 vectors in flight per thread for wide rows
-  if (nvec >= 512 && t > 512) t = 512;
+  int t = ((nvec + vec_per_thread - 1) / vec_per_thread + 31) / 32 * 32;
+  if (t > 512) t = 512;
+  while (t * kMaxVecPerThread < nvec) t += 32;
   return t < 32 ? 32 : t;
 }
 
