@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--input-len", type=int, default=512)
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tiny", "tiny128"])
+    ap.add_argument("--max-num-batched-tokens", type=int, default=8192, help="prefill token budget per engine step")
     ap.add_argument("--no-e2e", action="store_true", help="skip the HTTP end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-requests", type=int, default=2)
@@ -285,7 +286,7 @@ def run_ours(a):
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     mcfg = model_config(a.model)
     ecfg = EngineConfig(model=f"random:{a.model}", tensor_parallel_size=a.gpus, max_num_seqs=a.requests,
-                        max_num_batched_tokens=8192,
+                        max_num_batched_tokens=a.max_num_batched_tokens,
                         max_model_len=min(mcfg.max_position_embeddings, max(1024, a.input_len + a.output_len + 16)),
                         seed=0)
     t_init = time.perf_counter()
@@ -360,7 +361,7 @@ def run_ours(a):
                    if a.model == "llama3-8b" else f"{a.model} TP={a.gpus} {a.input_len}-in/{a.output_len}-out",
                    "requests_per_step": R, "concurrency": R, "weights": "seeded N(0,0.02) random init",
                    "prompts": "seeded uniform token ids, fresh per step (working set 16 GB weights >> 126 MB L2)",
-                   "parallelism": f"tp{a.gpus}", "max_num_batched_tokens": 8192,
+                   "parallelism": f"tp{a.gpus}", "max_num_batched_tokens": a.max_num_batched_tokens,
                    "inputs": "token ids staged through one pinned buffer per engine step"},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "clocks": clk, "roofline": roofline, "decode_roofline": decode_roof,
