@@ -288,6 +288,7 @@ def run_ours(a):
     ecfg = EngineConfig(model=f"random:{a.model}", tensor_parallel_size=a.gpus, max_num_seqs=a.requests,
                         max_num_batched_tokens=a.max_num_batched_tokens,
                         max_model_len=min(mcfg.max_position_embeddings, max(1024, a.input_len + a.output_len + 16)),
+                        enable_prefix_caching=False,    # every timed token is computed (same as the vLLM baseline run)
                         seed=0)
     t_init = time.perf_counter()
     engine = LLMEngine.from_engine_config(ecfg, mcfg=mcfg)
@@ -362,6 +363,7 @@ def run_ours(a):
                    "requests_per_step": R, "concurrency": R, "weights": "seeded N(0,0.02) random init",
                    "prompts": "seeded uniform token ids, fresh per step (working set 16 GB weights >> 126 MB L2)",
                    "parallelism": f"tp{a.gpus}", "max_num_batched_tokens": a.max_num_batched_tokens,
+                   "prefix_caching": False,
                    "inputs": "token ids staged through one pinned buffer per engine step"},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "clocks": clk, "roofline": roofline, "decode_roofline": decode_roof,

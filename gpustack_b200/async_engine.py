@@ -163,7 +163,8 @@ class _StreamHub:
 def engine_snapshot(engine) -> dict:
     s = engine.sched
     return {"running": s.num_running, "waiting": s.num_waiting, "kv_usage": s.kv_usage(),
-            "preemptions": s.num_preemptions, "generation_tokens": engine.counters["generation_tokens"]}
+            "preemptions": s.num_preemptions, "generation_tokens": engine.counters["generation_tokens"],
+            "prefix_queries": s.pool.queries, "prefix_hits": s.pool.hits}
 
 
 class AsyncEngine(_StreamHub):
@@ -282,7 +283,8 @@ class EngineClient(_StreamHub):
         super().__init__()
         self.conn = conn
         self._send_lock = threading.Lock()
-        self._snap = {"running": 0, "waiting": 0, "kv_usage": 0.0, "preemptions": 0, "generation_tokens": 0}
+        self._snap = {"running": 0, "waiting": 0, "kv_usage": 0.0, "preemptions": 0, "generation_tokens": 0,
+                      "prefix_queries": 0, "prefix_hits": 0}
         self._last_msg = time.monotonic()
         self._thread = threading.Thread(target=self._reader, name="b200-engine-client", daemon=True)
         self._thread.start()

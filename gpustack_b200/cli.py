@@ -41,6 +41,7 @@ def build_parser() -> argparse.ArgumentParser:
     s.add_argument("--max-num-batched-tokens", type=int, default=8192)
     s.add_argument("--num-gpu-blocks-override", type=int, default=None)
     s.add_argument("--enforce-eager", action="store_true")
+    s.add_argument("--enable-prefix-caching", action=argparse.BooleanOptionalAction, default=True)
     s.add_argument("--seed", type=int, default=0)
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
@@ -62,7 +63,8 @@ def _engine_config(args, tp: int):
                         max_model_len=args.max_model_len, tensor_parallel_size=tp,
                         gpu_memory_utilization=args.gpu_memory_utilization, max_num_seqs=args.max_num_seqs,
                         max_num_batched_tokens=args.max_num_batched_tokens,
-                        num_gpu_blocks=args.num_gpu_blocks_override, enforce_eager=args.enforce_eager, seed=args.seed)
+                        num_gpu_blocks=args.num_gpu_blocks_override, enforce_eager=args.enforce_eager,
+                        enable_prefix_caching=args.enable_prefix_caching, seed=args.seed)
 
 
 def make_engine(ecfg):

@@ -127,6 +127,7 @@ class EngineConfig:
     max_num_batched_tokens: int = 8192
     num_gpu_blocks: Optional[int] = None      # override the memory-derived KV block count
     enforce_eager: bool = False               # skip CUDA-graph capture of decode steps
+    enable_prefix_caching: bool = True        # reuse full KV blocks across requests (reference engine default)
     seed: int = 0
     block_size: int = 16
     cuda_graph_sizes: list = field(default_factory=list)

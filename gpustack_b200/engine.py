@@ -179,7 +179,7 @@ class LLMEngine:
         self.runner.init_kv_cache(n)
         self.runner.capture_graphs()
         self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
-                               ecfg.max_model_len, mcfg.eos_token_id)
+                               ecfg.max_model_len, mcfg.eos_token_id, ecfg.enable_prefix_caching)
         self.requests: Dict[str, Request] = {}
         self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
         self.step_time = {"prefill": 0.0, "decode": 0.0}

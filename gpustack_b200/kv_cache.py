@@ -1,23 +1,62 @@
-"""Paged KV-cache bookkeeping (host side): a free-list block pool and per-sequence block tables.
+"""Paged KV-cache bookkeeping (host side): a block pool with optional prefix caching.
 
 Counterpart of the reference engine's BlockPool / KVCacheManager
-($VLLM/v1/core/block_pool.py, $VLLM/v1/core/kv_cache_manager.py).  Blocks hold 16 tokens; the
-device tensors are [num_blocks][Hkv][16][D] per layer for K and for V (see csrc/attention.cu).
-Block 0 is reserved as the "null" block that padded block-table entries point to.
+($VLLM/v1/core/block_pool.py, $VLLM/v1/core/kv_cache_manager.py, hashing in
+$VLLM/v1/core/kv_cache_utils.py `hash_block_tokens`).  Blocks hold 16 tokens; the device tensors
+are [num_blocks][Hkv][16][D] per layer for K and for V (see csrc/attention.cu).  Block 0 is
+reserved as the "null" block that padded block-table entries point to.
+
+Prefix caching (GPUStack passes `--enable-prefix-caching` straight through,
+gpustack/worker/backends/vllm.py:602-639; on by default in the reference engine): every FULL block
+is keyed by a chained digest of (parent digest, its 16 token ids).  A finished or preempted
+sequence leaves its blocks in the free queue *with* their keys, so a later request whose prompt
+starts with the same tokens re-attaches them (ref-count + 1) and starts its prefill behind them.
+The free queue is LRU: a block loses its key only when it is handed out again.
 """
 from __future__ import annotations
 
-from collections import deque
-from typing import Deque, Dict, List
+import hashlib
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+_ROOT = b"b200-kv-root"
+
+
+def block_digests(token_ids: Sequence[int], block_size: int, have: Optional[List[bytes]] = None,
+                  upto_blocks: Optional[int] = None) -> List[bytes]:
+    """Chained 16-byte digests of the full blocks of `token_ids`; extends `have` in place."""
+    out = have if have is not None else []
+    n_full = len(token_ids) // block_size
+    if upto_blocks is not None:
+        n_full = min(n_full, upto_blocks)
+    if len(out) >= n_full:
+        return out
+    arr = np.asarray(token_ids[len(out) * block_size: n_full * block_size], dtype=np.int32)
+    parent = out[-1] if out else _ROOT
+    for i in range(n_full - len(out)):
+        h = hashlib.blake2b(parent, digest_size=16)
+        h.update(arr[i * block_size:(i + 1) * block_size].tobytes())
+        parent = h.digest()
+        out.append(parent)
+    return out
 
 
 class BlockPool:
-    def __init__(self, num_blocks: int, block_size: int = 16):
+    def __init__(self, num_blocks: int, block_size: int = 16, enable_prefix_caching: bool = False):
         if num_blocks < 2:
             raise ValueError("need at least 2 KV blocks")
         self.num_blocks = num_blocks
         self.block_size = block_size
-        self._free: Deque[int] = deque(range(1, num_blocks))  # block 0 = null block
+        self.caching = enable_prefix_caching
+        # free queue, head = next block handed out; block 0 = null block, never in the queue
+        self._free: "OrderedDict[int, None]" = OrderedDict((b, None) for b in range(1, num_blocks))
+        self._ref = [0] * num_blocks
+        self._key: List[Optional[bytes]] = [None] * num_blocks     # digest a block is cached under
+        self._cached: Dict[bytes, int] = {}
+        self.queries = 0          # tokens looked up / found, for vllm:prefix_cache_{queries,hits}
+        self.hits = 0
 
     @property
     def num_free(self) -> int:
@@ -26,6 +65,10 @@ class BlockPool:
     @property
     def num_total(self) -> int:
         return self.num_blocks - 1
+
+    @property
+    def num_cached(self) -> int:
+        return len(self._cached)
 
     def usage(self) -> float:
         return 1.0 - self.num_free / max(1, self.num_total)
@@ -36,11 +79,70 @@ class BlockPool:
     def allocate(self, n: int) -> List[int]:
         if n > len(self._free):
             raise MemoryError(f"KV cache exhausted: want {n} blocks, {len(self._free)} free")
-        return [self._free.popleft() for _ in range(n)]
+        out = []
+        for _ in range(n):
+            b, _ = self._free.popitem(last=False)
+            k = self._key[b]
+            if k is not None:                      # evicted from the prefix cache
+                del self._cached[k]
+                self._key[b] = None
+            self._ref[b] = 1
+            out.append(b)
+        return out
 
     def free(self, blocks: List[int]) -> None:
-        # most recently used blocks go back first so that hot L2 lines are reused
-        self._free.extendleft(reversed(blocks))
+        if self.caching:
+            # tail of the sequence first: it is evicted before the (more widely shared) head
+            for b in reversed(blocks):
+                self._ref[b] -= 1
+                if self._ref[b] == 0:
+                    self._free[b] = None
+            return
+        # no caching: most recently used blocks go back to the head so that hot L2 lines are reused
+        for b in reversed(blocks):
+            self._ref[b] -= 1
+            if self._ref[b] == 0:
+                self._free[b] = None
+                self._free.move_to_end(b, last=False)
+
+    # ------------------------------------------------------------------ prefix cache
+    def match_prefix(self, digests: Sequence[bytes]) -> List[int]:
+        """Longest run of cached blocks for the chained `digests` (no state change)."""
+        hit: List[int] = []
+        if not self.caching:
+            return hit
+        for d in digests:
+            b = self._cached.get(d)
+            if b is None:
+                break
+            hit.append(b)
+        return hit
+
+    def count_free(self, blocks: Sequence[int]) -> int:
+        """How many of `blocks` currently sit in the free queue (attaching them shrinks it)."""
+        return sum(1 for b in blocks if self._ref[b] == 0)
+
+    def attach(self, blocks: Sequence[int]) -> None:
+        """Take a reference on cached blocks returned by match_prefix."""
+        for b in blocks:
+            if self._ref[b] == 0:
+                del self._free[b]
+            self._ref[b] += 1
+
+    def register(self, blocks: Sequence[int], digests: Sequence[bytes]) -> None:
+        """Publish full, already-written blocks under their digests (first writer wins)."""
+        if not self.caching:
+            return
+        for b, d in zip(blocks, digests):
+            if self._key[b] is not None or d in self._cached:
+                continue
+            self._key[b] = d
+            self._cached[d] = b
+
+    def reset_prefix_cache(self) -> None:
+        for d, b in self._cached.items():
+            self._key[b] = None
+        self._cached.clear()
 
 
 class SequenceBlocks:
@@ -58,6 +160,9 @@ class SequenceBlocks:
 
 
 class KVCacheManager:
+    """Stand-alone block-table manager over a BlockPool (used by kernel tests and tools; the
+    scheduler keeps its tables in the persistent batch instead)."""
+
     def __init__(self, num_blocks: int, block_size: int = 16):
         self.pool = BlockPool(num_blocks, block_size)
         self.block_size = block_size

@@ -2,7 +2,7 @@
 
 Counterpart of the reference engine's Scheduler.schedule ($VLLM/v1/core/sched/scheduler.py:329):
 token-budgeted prefill batches (with chunking of long prompts), decode batches over every running
-sequence, block allocation / preemption through KVCacheManager.  Policy: prefill-first (best
+sequence, block allocation / prefix-cache reuse / preemption through the BlockPool.  Policy: prefill-first (best
 TTFT and throughput for the benchmark_serving.py workload), decode otherwise.
 
 Running sequences live in a compact "persistent batch" of numpy arrays (rows 0..B-1) so that a
@@ -18,7 +18,7 @@ from typing import Deque, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .kv_cache import BlockPool
+from .kv_cache import BlockPool, block_digests
 
 
 @dataclass
@@ -45,6 +45,8 @@ class Request:
     finished: bool = False
     finish_reason: Optional[str] = None
     num_preemptions: int = 0
+    digests: List[bytes] = field(default_factory=list)   # chained keys of the full KV blocks
+    num_cached_tokens: int = 0     # prompt tokens served from the prefix cache at admission
 
     @property
     def all_ids(self) -> List[int]:
@@ -82,8 +84,8 @@ class StepOutput:
 
 class Scheduler:
     def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: int, eos_token_id: Optional[int]):
-        self.pool = BlockPool(num_blocks, block_size)
+                 max_model_len: int, eos_token_id: Optional[int], enable_prefix_caching: bool = False):
+        self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching)
         self.block_size = block_size
         self.max_num_seqs = max_num_seqs
         self.max_tokens_per_step = max_num_batched_tokens
@@ -151,8 +153,18 @@ class Scheduler:
     def _blocks_for(self, ntok: int) -> int:
         return (ntok + self.block_size - 1) // self.block_size
 
+    def _publish(self, r: Request) -> None:
+        """Key the request's full, already-written blocks in the prefix cache."""
+        if not self.pool.caching or not r.blocks:
+            return
+        n_full = min(r.num_computed // self.block_size, len(r.blocks))
+        if n_full > len(r.digests):
+            block_digests(r.all_ids, self.block_size, r.digests, upto_blocks=n_full)
+        self.pool.register(r.blocks[:n_full], r.digests[:n_full])
+
     def _release(self, r: Request) -> None:
         if r.blocks:
+            self._publish(r)
             self.pool.free(r.blocks)
             r.blocks = []
 
@@ -183,17 +195,29 @@ class Scheduler:
             r = self.waiting[0]
             if len(self.rows) + len(self.prefilling) >= self.max_num_seqs:
                 break
-            need = self._blocks_for(r.prefill_target + 1)
+            target = r.prefill_target
+            hit: List[int] = []
+            if self.pool.caching:
+                # the last token is always recomputed: its logits are what gets sampled
+                block_digests(r.all_ids, self.block_size, r.digests, upto_blocks=(target - 1) // self.block_size)
+                hit = self.pool.match_prefix(r.digests[: (target - 1) // self.block_size])
+            need = self._blocks_for(target + 1) - len(hit)
             # keep one spare block per running sequence so that decode does not preempt at once
-            if need + len(self.rows) > self.pool.num_free:
+            if need + self.pool.count_free(hit) + len(self.rows) > self.pool.num_free:
                 break
             self.waiting.popleft()
-            r.blocks = self.pool.allocate(need)
-            r.num_computed = 0
+            self.pool.attach(hit)
+            r.blocks = hit + self.pool.allocate(need)
+            r.num_computed = len(hit) * self.block_size
+            if self.pool.caching:
+                self.pool.queries += target
+                self.pool.hits += r.num_computed
+                if r.num_preemptions == 0:
+                    r.num_cached_tokens = r.num_computed
             self.prefilling.append(r)
-            n = min(budget, r.prefill_target)
-            reqs.append(r); starts.append(0); lens.append(n)
-            sample.append(n == r.prefill_target)
+            n = min(budget, target - r.num_computed)
+            reqs.append(r); starts.append(r.num_computed); lens.append(n)
+            sample.append(r.num_computed + n == target)
             budget -= n
         if not reqs:
             return None
@@ -245,6 +269,7 @@ class Scheduler:
     def _evict_row(self, i: int) -> None:
         last = len(self.rows) - 1
         r = self.rows[i]
+        r.num_computed = int(self.num_computed[i])      # tokens whose K/V are in the cache
         if i != last:
             m = self.rows[last]
             self.rows[i] = m
@@ -271,6 +296,7 @@ class Scheduler:
         j = 0
         for r, n, smp in zip(plan.reqs, plan.lens, plan.sample):
             r.num_computed += n
+            self._publish(r)
             if not smp:
                 continue
             tok = int(sampled[j]); j += 1

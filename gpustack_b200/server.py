@@ -258,6 +258,10 @@ def render_metrics(aeng: AsyncEngine, model: str) -> str:
     gauge("vllm:gpu_cache_usage_perc", "KV-cache usage (legacy name).", round(snap["kv_usage"], 6))
     counter("vllm:num_preemptions", "Cumulative number of preemptions from the engine.", snap["preemptions"])
     counter("vllm:prompt_tokens", "Number of prefill tokens processed.", m.prompt_tokens)
+    counter("vllm:prefix_cache_queries", "Prefix cache queries, in terms of number of queried tokens.",
+            snap.get("prefix_queries", 0))
+    counter("vllm:prefix_cache_hits", "Prefix cache hits, in terms of number of cached tokens.",
+            snap.get("prefix_hits", 0))
     counter("vllm:generation_tokens", "Number of generation tokens processed.", snap["generation_tokens"])
     L.append("# HELP vllm:request_success Count of successfully processed requests.\n# TYPE vllm:request_success counter")
     for reason, n in m.success.items():

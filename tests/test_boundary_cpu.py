@@ -52,13 +52,15 @@ def test_vllm_custom_version_argv_is_accepted_with_injected_flags():
     vcfg = spec["version_configs"]["b200-custom"]
     argv = gc.build_vllm_command_args(vcfg, "/models/l3", 40010, "10.1.1.1", "l3", gpu_count=8,
                                       derived_max_model_len=131072,
-                                      backend_parameters=["--gpu-memory-utilization 0.85", "--enable-prefix-caching"])
+                                      backend_parameters=["--gpu-memory-utilization 0.85", "--no-enable-prefix-caching",
+                                                          "--enable-expert-parallel"])
     assert argv[:3] == ["b200-engine", "serve", "/models/l3"]
     assert argv[3:7] == ["--max-model-len", "8192", "--tensor-parallel-size", "8"]
     args, unknown = build_parser().parse_known_args(argv[1:])
     assert args.tensor_parallel_size == "8" and args.max_model_len == 8192 and args.port == 40010
     assert args.gpu_memory_utilization == 0.85
-    assert unknown == ["--enable-prefix-caching"]     # tolerated (warned about), not fatal
+    assert args.enable_prefix_caching is False
+    assert unknown == ["--enable-expert-parallel"]    # tolerated (warned about), not fatal
     # user-set parallelism / host are respected, not duplicated
     argv = gc.build_vllm_command_args(vcfg, "/m", 1, "h", "n", gpu_count=4, backend_parameters=["-tp 2", "--host 0.0.0.0"])
     assert "--tensor-parallel-size" not in argv and argv.count("--host") == 1

@@ -114,3 +114,32 @@ def test_temperature_sampling_is_seeded_and_differs_from_greedy():
     # top_p -> 0 keeps only the most likely token = greedy
     d = eng.generate([p], SamplingParams(max_tokens=16, ignore_eos=True, temperature=1.0, top_p=1e-6, seed=1))[0]
     assert d == greedy
+
+
+def test_prefix_caching_matches_uncached_run():
+    """Requests sharing a head re-attach its KV blocks (prefill starts behind them) and still
+    produce the tokens of a cache-less engine; a repeated conversation turn hits on generated
+    tokens as well."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    g = torch.Generator().manual_seed(21)
+    head = torch.randint(3, 500, (80,), generator=g).tolist()
+    tails = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (7, 30, 1, 45)]
+    prompts = [head + t for t in tails]
+    sp = SamplingParams(max_tokens=24, ignore_eos=True)
+    eng_off, _ = _engine(O.TINY, enforce_eager=True, enable_prefix_caching=False)
+    ref = [eng_off.generate([p], sp)[0] for p in prompts]
+    ref_turn2 = eng_off.generate([prompts[0] + ref[0] + [5, 6, 7]], sp)[0]
+    del eng_off
+    eng, _ = _engine(O.TINY, enforce_eager=True, enable_prefix_caching=True)
+    got = [eng.generate([prompts[0]], sp)[0]]
+    assert eng.sched.pool.hits == 0
+    got += eng.generate(prompts[1:], sp)                    # three requests, all hit the 5 head blocks
+    assert eng.sched.pool.hits == 3 * 80
+    got_turn2 = eng.generate([prompts[0] + got[0] + [5, 6, 7]], sp)[0]
+    assert eng.sched.pool.hits >= 3 * 80 + 96               # prompt + generated tokens of turn 1
+    for a, b in zip(ref + [ref_turn2], got + [got_turn2]):
+        assert a[0] == b[0]
+        agree = sum(x == y for x, y in zip(a, b)) / len(a)
+        assert agree >= 0.9 or a[: len(a) // 2] == b[: len(b) // 2]
+    assert eng.sched.pool.num_free == eng.sched.pool.num_total

@@ -122,3 +122,205 @@ def test_persistent_batch_stays_compact_after_eviction():
         for r in s.rows:
             assert s.block_table[r.row, : len(r.blocks)].tolist() == r.blocks
             assert s.num_computed[r.row] == len(r.prompt_ids) + len(r.output_ids) - 1
+
+
+# ---------------------------------------------------------------------------- prefix caching
+def mkc(num_blocks=64, max_seqs=8, budget=256, max_len=512, eos=2):
+    return Scheduler(num_blocks, 16, max_seqs, budget, max_len, eos, enable_prefix_caching=True)
+
+
+def run_to_completion(s, tok=7):
+    n = 0
+    while s.has_work():
+        drive(s, s.schedule(), tok)
+        n += 1
+        assert n < 10_000
+    return n
+
+
+def test_block_digests_chain_and_extend():
+    from gpustack_b200.kv_cache import block_digests
+
+    a = block_digests(list(range(40)), 16)
+    assert len(a) == 2 and len(a[0]) == 16 and a[0] != a[1]
+    b = block_digests(list(range(48)), 16, have=list(a))
+    assert b[:2] == a and len(b) == 3
+    c = block_digests([9] + list(range(1, 48)), 16)
+    assert c[0] != b[0] and c[1] != b[1] and c[2] != b[2]        # a different head changes every key
+    assert block_digests(list(range(48)), 16, upto_blocks=1) == a[:1]
+
+
+def test_prefix_cache_hit_skips_cached_blocks_and_shares_them():
+    s = mkc()
+    prompt = list(range(3, 3 + 50))                               # 3 full blocks + 2 tokens
+    s.add(Request("a", list(prompt), SamplingParams(max_tokens=2, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [0] and p.lens == [50]
+    a_blocks = list(p.reqs[0].blocks)
+    drive(s, p)
+    run_to_completion(s)
+    assert s.pool.num_free == s.pool.num_total and s.pool.num_cached == 3
+    # same prompt again + a request sharing only the first 2 blocks
+    s.add(Request("b", list(prompt), SamplingParams(max_tokens=2, ignore_eos=True)))
+    s.add(Request("c", prompt[:32] + [400] * 30, SamplingParams(max_tokens=2, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [48, 32] and p.lens == [2, 30] and p.sample == [True, True]
+    rb, rc = p.reqs
+    assert rb.blocks[:3] == a_blocks[:3] and rc.blocks[:2] == a_blocks[:2] and rc.blocks[2] != rb.blocks[2]
+    assert rb.num_cached_tokens == 48 and rc.num_cached_tokens == 32
+    assert s.pool.hits == 80 and s.pool.queries == 50 + 50 + 62
+    run_to_completion(s)
+    assert s.pool.num_free == s.pool.num_total
+
+
+def test_prefix_cache_never_covers_the_last_prompt_token():
+    s = mkc()
+    prompt = list(range(3, 3 + 32))                               # exactly 2 full blocks
+    s.add(Request("a", list(prompt), SamplingParams(max_tokens=1, ignore_eos=True)))
+    run_to_completion(s)
+    s.add(Request("b", list(prompt), SamplingParams(max_tokens=1, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [16] and p.lens == [16] and p.sample == [True]   # last block recomputed for its logits
+
+
+def test_generated_tokens_are_cached_for_the_next_turn():
+    s = mkc()
+    prompt = list(range(3, 3 + 20))
+    s.add(Request("a", list(prompt), SamplingParams(max_tokens=30, ignore_eos=True)))
+    run_to_completion(s, tok=7)
+    # K/V in the cache at the end: 20 prompt + 29 generated tokens = 49 -> 3 full blocks
+    assert s.pool.num_cached == 3
+    turn2 = prompt + [7] * 30 + [11, 12, 13]
+    s.add(Request("b", turn2, SamplingParams(max_tokens=1, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [48] and p.lens == [5]
+
+
+def test_cached_blocks_are_evicted_lru_and_only_when_needed():
+    s = mkc(num_blocks=9, budget=512)                             # 8 usable blocks
+    s.add(Request("a", list(range(100, 148)), SamplingParams(max_tokens=1, ignore_eos=True)))   # 3 full + spare
+    run_to_completion(s)
+    assert s.pool.num_cached == 3 and s.pool.num_free == 8
+    s.add(Request("b", list(range(200, 264)), SamplingParams(max_tokens=1, ignore_eos=True)))   # needs 5 blocks
+    run_to_completion(s)
+    # 8 blocks, b took 5: the never-keyed spare block of `a` + fresh ones go first; a's head survives
+    s.add(Request("c", list(range(100, 148)), SamplingParams(max_tokens=1, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts[0] >= 16                                      # at least the first block of `a` is still cached
+    run_to_completion(s)
+    # now force eviction of everything: a prompt that needs all 8 blocks
+    s.add(Request("d", list(range(300, 300 + 120)), SamplingParams(max_tokens=1, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [0] and p.lens == [120]
+    assert s.pool.num_cached == 0
+    run_to_completion(s)
+    assert s.pool.num_free == s.pool.num_total and s.pool.num_cached == 7
+
+
+def test_preempted_request_reattaches_its_own_blocks():
+    s = mkc(num_blocks=8, max_seqs=4, budget=256, max_len=256)     # 7 usable blocks
+    s.add(Request("a", list(range(10, 42)), SamplingParams(max_tokens=64, ignore_eos=True)))
+    s.add(Request("b", list(range(50, 82)), SamplingParams(max_tokens=64, ignore_eos=True)))
+    pre = 0
+    steps = 0
+    seen_restart = None
+    while s.has_work():
+        plan = s.schedule()
+        if isinstance(plan, PrefillPlan) and any(r.num_preemptions for r in plan.reqs):
+            seen_restart = (plan.starts[0], plan.lens[0])
+        drive(s, plan)
+        steps += 1
+        assert steps < 2000
+    assert s.num_preemptions >= 1
+    assert seen_restart is not None and seen_restart[0] >= 16       # recompute resumes behind its surviving blocks
+    assert s.pool.num_free == s.pool.num_total
+
+
+def test_shared_block_refcounts_survive_one_owner_finishing():
+    s = mkc()
+    prompt = list(range(3, 3 + 40))
+    s.add(Request("a", list(prompt), SamplingParams(max_tokens=1, ignore_eos=True)))
+    run_to_completion(s)
+    s.add(Request("b", list(prompt), SamplingParams(max_tokens=3, ignore_eos=True)))
+    s.add(Request("c", list(prompt), SamplingParams(max_tokens=9, ignore_eos=True)))
+    p = s.schedule()
+    rb, rc = p.reqs
+    shared = rb.blocks[:2]
+    assert rc.blocks[:2] == shared and all(s.pool._ref[b] == 2 for b in shared)
+    drive(s, p)
+    while not rb.finished:
+        drive(s, s.schedule())
+    assert all(s.pool._ref[b] == 1 for b in shared) and not rc.finished
+    assert all(b not in s.pool._free for b in shared)
+    run_to_completion(s)
+    assert all(s.pool._ref[b] == 0 for b in shared) and s.pool.num_free == s.pool.num_total
+
+
+def test_disabled_prefix_caching_never_reuses():
+    s = mk()
+    prompt = list(range(3, 3 + 50))
+    s.add(Request("a", list(prompt), SamplingParams(max_tokens=1, ignore_eos=True)))
+    while s.has_work():
+        drive(s, s.schedule())
+    s.add(Request("b", list(prompt), SamplingParams(max_tokens=1, ignore_eos=True)))
+    p = s.schedule()
+    assert p.starts == [0] and p.lens == [50] and s.pool.num_cached == 0
+
+
+def test_prefix_cache_randomised_content_model():
+    """Model the device cache as token ids per slot: whatever the scheduler plans, the context a
+    chunk attends to must hold exactly the request's own tokens, shared blocks must never be
+    written, and the ref counts must equal the number of live owners."""
+    rng = np.random.RandomState(0)
+    BS = 16
+    s = Scheduler(40, BS, 6, 96, 400, 2, enable_prefix_caching=True)
+    store = np.full((40, BS), -1, dtype=np.int64)
+    heads = [rng.randint(3, 500, size=n).tolist() for n in (16, 48, 70, 33)]
+    live, nreq, steps = {}, 0, 0
+    while steps < 1500:
+        steps += 1
+        if nreq < 120 and rng.rand() < 0.35:
+            h = heads[rng.randint(len(heads))]
+            tail = rng.randint(3, 500, size=rng.randint(1, 40)).tolist()
+            r = Request(f"q{nreq}", h[: rng.randint(1, len(h) + 1)] + tail,
+                        SamplingParams(max_tokens=int(rng.randint(1, 40)), ignore_eos=True))
+            s.add(r); live[r.req_id] = r; nreq += 1
+        plan = s.schedule()
+        if plan is None:
+            if nreq >= 120:
+                break
+            continue
+        if isinstance(plan, PrefillPlan):
+            for r, st, n in zip(plan.reqs, plan.starts, plan.lens):
+                ids = r.all_ids
+                for pos in range(st):                            # context the chunk will read
+                    assert store[r.blocks[pos // BS], pos % BS] == ids[pos], (r.req_id, pos)
+                for pos in range(st, st + n):                    # K/V the chunk writes
+                    b = r.blocks[pos // BS]
+                    assert s.pool._ref[b] == 1 or store[b, pos % BS] == ids[pos], "write into a shared block"
+                    store[b, pos % BS] = ids[pos]
+            toks = rng.randint(3, 500, size=sum(plan.sample)).tolist()
+            s.update_prefill(plan, toks)
+        else:
+            B = plan.batch
+            for i in range(B):
+                r = s.rows[i]
+                pos = int(s.num_computed[i])
+                b = int(s.block_table[i, pos // BS])
+                assert b == r.blocks[pos // BS] and s.pool._ref[b] == 1
+                for q in range(pos):
+                    assert store[int(s.block_table[i, q // BS]), q % BS] == r.all_ids[q]
+                store[b, pos % BS] = int(s.last_token[i])
+                assert int(s.last_token[i]) == r.all_ids[pos]
+            s.update_decode(plan, rng.randint(3, 500, size=B).astype(np.int32))
+        # ref counts == number of live owners; free queue == exactly the unreferenced blocks
+        owners = np.zeros(40, dtype=int)
+        for r in list(s.prefilling) + [x for x in s.rows if x is not None]:
+            for b in r.blocks:
+                owners[b] += 1
+        assert owners[1:].tolist() == s.pool._ref[1:]
+        assert set(s.pool._free) == {b for b in range(1, 40) if owners[b] == 0}
+        for d, b in s.pool._cached.items():
+            assert s.pool._key[b] == d
+    assert nreq == 120 and not s.has_work() and s.pool.hits > 0
+    assert all(r.finished for r in live.values())
