@@ -21,6 +21,7 @@ SOURCES = [
     "rope_kv.cu",
     "elementwise.cu",
     "gemm_tcgen05.cu",
+    "quant_fp8.cu",
     "attention.cu",
     "allreduce.cu",
 ]

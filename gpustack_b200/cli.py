@@ -43,6 +43,7 @@ def build_parser() -> argparse.ArgumentParser:
     s.add_argument("--enforce-eager", action="store_true")
     s.add_argument("--enable-prefix-caching", action=argparse.BooleanOptionalAction, default=True)
     s.add_argument("--seed", type=int, default=0)
+    s.add_argument("--quantization", "-q", default=None, choices=[None, "fp8"])
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
     w = sub.add_parser("_worker", help=argparse.SUPPRESS)
@@ -64,7 +65,8 @@ def _engine_config(args, tp: int):
                         gpu_memory_utilization=args.gpu_memory_utilization, max_num_seqs=args.max_num_seqs,
                         max_num_batched_tokens=args.max_num_batched_tokens,
                         num_gpu_blocks=args.num_gpu_blocks_override, enforce_eager=args.enforce_eager,
-                        enable_prefix_caching=args.enable_prefix_caching, seed=args.seed)
+                        enable_prefix_caching=args.enable_prefix_caching, quantization=args.quantization,
+                        seed=args.seed)
 
 
 def make_engine(ecfg):

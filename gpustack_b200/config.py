@@ -33,6 +33,7 @@ class ModelConfig:
     architecture: str = "LlamaForCausalLM"
     eos_token_id: Optional[int] = None
     bos_token_id: Optional[int] = None
+    quantization: Optional[str] = None       # "fp8" when config.json carries an fp8 quantization_config
 
     @property
     def q_size(self) -> int:
@@ -68,7 +69,18 @@ class ModelConfig:
         scaling = d.get("rope_scaling") or (d.get("rope_parameters") or {}).get("rope_type")
         if isinstance(scaling, dict) and scaling.get("rope_type", scaling.get("type")) not in (None, "default"):
             raise ValueError("rope_scaling other than default is not supported yet")
+        quant = None
+        qc = d.get("quantization_config")
+        if isinstance(qc, dict):
+            # per-tensor fp8 checkpoints with dynamic activation scales (what `--quantization fp8`
+            # produces and what $VLLM/.../quantization/fp8.py:80-140 reads); anything else is refused
+            method = qc.get("quant_method")
+            if method != "fp8" or qc.get("activation_scheme", "dynamic") != "dynamic" or qc.get("weight_block_size"):
+                raise ValueError(f"unsupported quantization_config {qc}: only quant_method=fp8, "
+                                 "activation_scheme=dynamic, per-tensor weights are supported")
+            quant = "fp8"
         return ModelConfig(
+            quantization=quant,
             vocab_size=d["vocab_size"], hidden_size=d["hidden_size"],
             intermediate_size=d["intermediate_size"], num_hidden_layers=d["num_hidden_layers"],
             num_attention_heads=heads, num_key_value_heads=d.get("num_key_value_heads", heads),
@@ -85,7 +97,10 @@ class ModelConfig:
             return ModelConfig.from_dict(json.load(f))
 
     def to_hf_dict(self) -> dict:
+        extra = {"quantization_config": {"quant_method": "fp8", "activation_scheme": "dynamic"}} \
+            if self.quantization == "fp8" else {}
         return {
+            **extra,
             "architectures": [self.architecture], "model_type": "llama", "vocab_size": self.vocab_size,
             "hidden_size": self.hidden_size, "intermediate_size": self.intermediate_size,
             "num_hidden_layers": self.num_hidden_layers, "num_attention_heads": self.num_attention_heads,
@@ -128,6 +143,7 @@ class EngineConfig:
     num_gpu_blocks: Optional[int] = None      # override the memory-derived KV block count
     enforce_eager: bool = False               # skip CUDA-graph capture of decode steps
     enable_prefix_caching: bool = True        # reuse full KV blocks across requests (reference engine default)
+    quantization: Optional[str] = None        # None | "fp8" (W8A8: online per-tensor weights, per-token activations)
     seed: int = 0
     block_size: int = 16
     cuda_graph_sizes: list = field(default_factory=list)

@@ -253,6 +253,19 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, 
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 elements per instruction)
+__device__ __forceinline__ void umma_e4m3_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
@@ -333,6 +346,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// kind::f8f6f4 instruction descriptor: e4m3 x e4m3 -> fp32 (a/b format 0), both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ cp.async

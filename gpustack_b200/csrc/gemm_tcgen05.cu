@@ -79,10 +79,14 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
 
 // TMEM accumulator (this warp's 32 lanes x BLOCK_X columns) -> global memory.
 // EPI 0: bf16 / fp32 store; EPI 1: SiLU*mul of interleaved gate/up rows (see the kernel comment).
-template <int BLOCK_X, int EPI>
+// FP8 1: W8A8 dequantisation -- every accumulator is multiplied by the token's dynamic activation
+//        scale xs[m] and the weight row's scale ws (already loaded by the caller) before any
+//        rounding, as cutlass_scaled_mm does in the reference engine.
+template <int BLOCK_X, int EPI, int FP8 = 0>
 __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, size_t split_off, int n,
                                                     int m_base, int M, int N, int64_t ldy, int out_f32,
-                                                    int lane) {
+                                                    int lane, const float* __restrict__ xs = nullptr,
+                                                    float ws = 1.f) {
   bf16* Yb = reinterpret_cast<bf16*>(Yv);
   float* Yf = reinterpret_cast<float*>(Yv);
   constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
@@ -92,7 +96,17 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, s
     uint32_t r[CH];
     if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, r);
     else tmem_ld_32x16(t_addr + c0, r);
+    float xs_lane = 0.f;
+    if constexpr (FP8) {
+      const int m = m_base + c0 + lane;   // lane j holds the scale of column j of this chunk
+      xs_lane = (lane < CH && m < M) ? xs[m] : 0.f;
+    }
     tmem_ld_wait();
+    if constexpr (FP8) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        r[j] = __float_as_uint(__uint_as_float(r[j]) * (__shfl_sync(0xffffffffu, xs_lane, j) * ws));
+    }
     if constexpr (EPI == 1) {
       const int ch = n >> 1;          // output channel of this lane pair
       bf16* dst = Yb + (size_t)(m_base + c0) * ldy + ch;
@@ -300,13 +314,18 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BLOCK_X, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
-                             int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
-                             int m_tiles, int group_m) {
+// FP8 1: e4m3 x e4m3 -> fp32 (kind::f8f6f4).  A k-block is still one 128-byte swizzle row, i.e.
+// 128 elements instead of 64, and one MMA consumes 32 bytes of K either way, so the pipeline is
+// byte-for-byte the bf16 one; only the element counts handed to TMA, the instruction kind and the
+// dequantising epilogue differ.
+template <int BLOCK_X, int EPI, int FP8>
+__device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_x,
+                                              void* __restrict__ Yv, int M, int N, int K, int64_t ldy,
+                                              int out_f32, int splits, int n_tiles, int m_tiles,
+                                              int group_m, const float* __restrict__ xscale,
+                                              const float* __restrict__ wscale, int wscale_stride) {
   using Cfg = Gemm2Cfg<BLOCK_X>;
+  constexpr int kElemsK = FP8 ? 2 * kBlockK : kBlockK;   // elements per 128-byte k-block
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -347,7 +366,7 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  const int kb_per_split = (K / kBlockK) / splits;
+  const int kb_per_split = (K / kElemsK) / splits;
   const int n_units = (n_tiles + 1) / 2;  // a unit = a pair of adjacent weight tiles (256 rows)
   const int total_units = n_units * m_tiles * splits;
   const int first_unit = (int)(blockIdx.x / 2);
@@ -362,15 +381,15 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
       for (int u = first_unit; u < total_units; u += unit_stride) {
         const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
         const int n_tile = c.n_tile * 2 + (int)crank;
-        const int k0 = c.split * kb_per_split * kBlockK;
+        const int k0 = c.split * kb_per_split * kElemsK;
         for (int kb = 0; kb < kb_per_split; ++kb) {
           mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
           uint8_t* a = smem + stage * Cfg::kStageBytes;
           uint8_t* b = a + Cfg::kABytes;
           // this CTA's bytes are announced on the LEADER's barrier, where the TMAs complete
           mbar_expect_tx_cluster(mapa_u32(&full_bar[stage], 0), Cfg::kStageBytes);
-          tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kBlockK, n_tile * kBlockW, hint_w);
-          tma_load_2d_2sm(b, &tmap_x, &full_bar[stage], k0 + kb * kBlockK,
+          tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kElemsK, n_tile * kBlockW, hint_w);
+          tma_load_2d_2sm(b, &tmap_x, &full_bar[stage], k0 + kb * kElemsK,
                           c.m_tile * BLOCK_X + (int)crank * Cfg::kHalf, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -379,7 +398,7 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockW, BLOCK_X);
+      constexpr uint32_t idesc = FP8 ? umma_idesc_e4m3(2 * kBlockW, BLOCK_X) : umma_idesc_bf16(2 * kBlockW, BLOCK_X);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -394,9 +413,13 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
-                          umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {   // 4 MMAs x 32 bytes of K per k-block
+            if constexpr (FP8)
+              umma_e4m3_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                            umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
+            else
+              umma_bf16_2sm(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                            umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0);
           }
           umma_commit_2sm_mc(&empty_bar[stage], 3);  // both CTAs' slots are free once these retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -418,7 +441,13 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
       const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
-      epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
+      if constexpr (FP8) {
+        const float ws = n < N ? wscale[(size_t)n * wscale_stride] : 0.f;
+        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane,
+                                             xscale, ws);
+      } else {
+        epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
@@ -433,6 +462,31 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BLOCK_X, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
+                             int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
+                             int m_tiles, int group_m) {
+  gemm_2sm_body<BLOCK_X, EPI, 0>(tmap_w, tmap_x, Yv, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
+                                 group_m, nullptr, nullptr, 0);
+}
+
+// W8A8 projection of the fp8 checkpoints GPUStack deploys (BASELINE config "Llama-3-70B fp8"):
+// Y[m,n] = (sum_k Xq[m,k] * Wq[n,k]) * xscale[m] * wscale[n * wscale_stride]
+// (reference operator: cutlass_scaled_mm behind Fp8LinearMethod.apply,
+// $VLLM/model_executor/layers/quantization/fp8.py:437-470).
+template <int BLOCK_X, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_fp8_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                            const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
+                            int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
+                            int m_tiles, int group_m, const float* __restrict__ xscale,
+                            const float* __restrict__ wscale, int wscale_stride) {
+  gemm_2sm_body<BLOCK_X, EPI, 1>(tmap_w, tmap_x, Yv, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
+                                 group_m, xscale, wscale, wscale_stride);
 }
 
 static int g_gemm_multicast = -1;  // -1: read B200_GEMM_MULTICAST once (default on)
@@ -530,6 +584,43 @@ static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, 
     return B200_ERR_CUDA;
   }
   return b200_check_launch("b200_gemm_bf16(2sm)");
+}
+
+template <int BLOCK_X, int EPI>
+static int launch_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx, int64_t ldw,
+                           int64_t ldy, int out_f32, int splits, const float* xscale, const float* wscale,
+                           int wscale_stride, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BLOCK_X>;
+  auto kernel = gemm_fp8_tcgen05_2sm_kernel<BLOCK_X, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      b200_set_error("gemm(fp8): cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return B200_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_tmap_u8_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBlockW, 2 * kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_u8_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, 2 * kBlockK);
+  if (rc) return rc;
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
+  const int total = ((n_tiles + 1) / 2) * m_tiles * splits;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int clusters = total < sms / 2 ? total : sms / 2;
+  const int group_m = gemm_group_m(m_tiles);
+  cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
+                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m, xscale, wscale,
+                             wscale_stride);
+  if (e != cudaSuccess) {
+    b200_set_error("b200_gemm_fp8: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200_ERR_CUDA;
+  }
+  return b200_check_launch("b200_gemm_fp8");
 }
 
 template <int BLOCK_X, int EPI = 0>
@@ -657,4 +748,45 @@ extern "C" int b200_gemm_bf16(const void* X, const void* W, void* Y, int M, int 
                               int64_t ldx, int64_t ldw, int64_t ldy, int out_f32, int splits,
                               void* stream) {
   return b200_gemm_bf16_ex(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, 0, stream);
+}
+
+// W8A8 fp8 (e4m3) projection.  X [M,K] and W [N,K] are e4m3 bytes, xscale [M] the dynamic per-token
+// activation scales, wscale the weight scale(s): stride 0 = per-tensor, 1 = per output channel.
+// silu_mul != 0 applies the fused SiLU*mul epilogue over interleaved gate/up rows (Y is [M, N/2]).
+extern "C" int b200_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
+                             int64_t ldw, int64_t ldy, const float* xscale, const float* wscale,
+                             int wscale_stride, int out_f32, int splits, int silu_mul, void* stream) {
+  constexpr int kElems = 2 * kBlockK;
+  B200_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_fp8: bad shape M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(K % kElems == 0, "gemm_fp8: K=%d must be a multiple of %d", K, kElems);
+  B200_REQUIRE(N > kBlockW, "gemm_fp8: N=%d must exceed %d (CTA-pair tiles)", N, kBlockW);
+  B200_REQUIRE(splits >= 1 && (K / kElems) % splits == 0, "gemm_fp8: splits=%d must divide K/%d=%d", splits,
+               kElems, K / kElems);
+  B200_REQUIRE(splits == 1 || out_f32, "gemm_fp8: split-K output must be fp32 partials");
+  B200_REQUIRE(!silu_mul || (splits == 1 && !out_f32 && N % 2 == 0), "gemm_fp8: silu_mul needs bf16 output, no split-K");
+  B200_REQUIRE(ldx >= K && ldw >= K && ldy >= (silu_mul ? N / 2 : N), "gemm_fp8: leading dimensions too small");
+  B200_REQUIRE(xscale && wscale && (wscale_stride == 0 || wscale_stride == 1), "gemm_fp8: bad scale arguments");
+  if (M == 0) return B200_OK;
+  const DeviceInfo& d = device_info();
+  if (!d.valid || d.cc_major != 10) {
+    b200_set_error("gemm_fp8: tcgen05 kernel needs an sm_100 device (found cc %d.%d)", d.cc_major, d.cc_minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int bx = plan_block_x(M, N, splits);
+  if (bx < 32) bx = 32;
+#define B200_FP8_CASE(BX)                                                                                   \
+  case BX:                                                                                                  \
+    return silu_mul ? launch_gemm_fp8<BX, 1>(X, W, Y, M, N, K, ldx, ldw, ldy, 0, 1, xscale, wscale,         \
+                                             wscale_stride, s)                                              \
+                    : launch_gemm_fp8<BX, 0>(X, W, Y, M, N, K, ldx, ldw, ldy, out_f32, splits, xscale,      \
+                                             wscale, wscale_stride, s);
+  switch (bx) {
+    B200_FP8_CASE(32)
+    B200_FP8_CASE(64)
+    B200_FP8_CASE(128)
+    default:
+      B200_FP8_CASE(256)
+  }
+#undef B200_FP8_CASE
 }

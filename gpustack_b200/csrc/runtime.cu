@@ -79,23 +79,37 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows, uint32_t box_cols, int elem_bytes);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, base, rows, cols, ld_elems, box_rows, box_cols, 2);
+}
+
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                    uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, base, rows, cols, ld_elems, box_rows, box_cols, 1);
+}
+
+static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows, uint32_t box_cols, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     b200_set_error("cuTensorMapEncodeTiled entry point not available");
     return B200_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld_elems * 2) & 15)) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld_elems * elem_bytes) & 15)) {
     b200_set_error("TMA operand must be 16-byte aligned (base %p, ld %llu elems)", base,
                    (unsigned long long)ld_elems);
     return B200_ERR_INVALID;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                  const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

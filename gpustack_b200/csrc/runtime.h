@@ -20,6 +20,10 @@ const DeviceInfo& device_info();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
 
+// Same over a byte matrix (fp8 operands): box_cols bytes must be 128.
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                    uint32_t box_rows, uint32_t box_cols);
+
 // B200_PDL=0 disables programmatic dependent launch (default on).
 bool pdl_enabled();
 

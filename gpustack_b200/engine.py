@@ -198,11 +198,15 @@ class LLMEngine:
         device = f"cuda:{torch.cuda.current_device()}"
         if state_dict is None and mcfg is None:
             mcfg = ModelConfig.from_pretrained(ecfg.model)
-            weights = load_safetensors_dir(mcfg, ecfg.model, rank, ecfg.tensor_parallel_size, device)
+            quant = ecfg.quantization or mcfg.quantization      # CLI flag, else the checkpoint's own config
+            weights = load_safetensors_dir(mcfg, ecfg.model, rank, ecfg.tensor_parallel_size, device,
+                                           quantization=quant)
         else:
             if state_dict is None:
                 state_dict = random_state_dict(mcfg, seed=ecfg.seed, device=device)
-            weights = shard_state_dict(mcfg, lambda k: state_dict[k], rank, ecfg.tensor_parallel_size, device)
+            weights = shard_state_dict(mcfg, lambda k: state_dict[k], rank, ecfg.tensor_parallel_size, device,
+                                       quantization=ecfg.quantization or mcfg.quantization,
+                                       has=lambda k: k in state_dict)
             del state_dict
             torch.cuda.empty_cache()
         return cls(mcfg, ecfg, weights, tp=tp, device=device)

@@ -207,6 +207,45 @@ def gemm_silu_mul(x, w_interleaved, out=None):
     return out
 
 
+# --------------------------------------------------------------------------------------- fp8 (W8A8)
+FP8 = torch.float8_e4m3fn
+
+
+def quant_fp8_per_token(x, out=None, scales=None):
+    """Dynamic per-token e4m3 quantisation: returns (q [T,K] float8_e4m3fn, scales [T] fp32)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.stride(-1) != 1:
+        raise B200Error("quant_fp8_per_token: bf16 CUDA tensor with contiguous rows required")
+    T, K = x.shape
+    q = torch.empty((T, K), dtype=FP8, device=x.device) if out is None else out
+    sc = torch.empty((T,), dtype=torch.float32, device=x.device) if scales is None else scales
+    check(load().b200_quant_fp8_per_token(_p(x), x.stride(0), _p(q), q.stride(0), _p(sc), T, K, _stream()),
+          "quant_fp8_per_token")
+    return q, sc
+
+
+def gemm_fp8(xq, xscale, wq, wscale, out=None, out_dtype=torch.bfloat16, splits: int = 1, silu_mul: bool = False):
+    """y = (xq @ wq.T) * xscale[:,None] * wscale  (e4m3 operands, fp32 accumulate).  wscale: fp32
+    tensor with 1 element (per-tensor) or N elements (per output channel).  silu_mul: wq holds
+    interleaved gate/up rows and y = silu(gate) * up, [M, N/2] bf16."""
+    if not (xq.is_cuda and wq.is_cuda) or xq.dtype != FP8 or wq.dtype != FP8:
+        raise B200Error("gemm_fp8: float8_e4m3fn CUDA tensors required (there is no CPU path)")
+    if xq.stride(-1) != 1 or wq.stride(-1) != 1:
+        raise B200Error("gemm_fp8: K must be the contiguous dimension")
+    _req(xscale, torch.float32, "xscale"); _req(wscale, torch.float32, "wscale")
+    M, K = xq.shape
+    N = wq.shape[0]
+    if xscale.numel() != M or wscale.numel() not in (1, N):
+        raise B200Error("gemm_fp8: xscale must have M elements, wscale 1 or N")
+    out_f32 = 1 if (out_dtype == torch.float32 or splits > 1) else 0
+    if out is None:
+        shape = (splits, M, N) if splits > 1 else (M, N // 2 if silu_mul else N)
+        out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device=xq.device)
+    check(load().b200_gemm_fp8(_p(xq), _p(wq), _p(out), M, N, K, xq.stride(0), wq.stride(0), out.stride(-2),
+                               _p(xscale), _p(wscale), 0 if wscale.numel() == 1 else 1, out_f32, splits,
+                               1 if silu_mul else 0, _stream()), "gemm_fp8")
+    return out
+
+
 def splitk_reduce(partials, out=None):
     _req(partials, torch.float32, "partials")
     S, M, N = partials.shape

@@ -58,6 +58,7 @@ class ModelRunner:
         self.max_tokens = max(ecfg.max_num_batched_tokens, self.max_seqs)
         self.prefill_tile = ops.attn_prefill_tile(self.Hq, self.Hkv)
         self.v_local = weights.lm_head.shape[0]
+        self.fp8 = weights.layers[0].qkv.dtype == ops.FP8
         self._alloc_workspace()
         self.k_cache: List[torch.Tensor] = []
         self.v_cache: List[torch.Tensor] = []
@@ -86,6 +87,10 @@ class ModelRunner:
         self.qkv = e(T, self.qkv_width)
         self.attn_out = e(T, self.Hq * self.D)
         self.act = e(T, self.I)
+        if self.fp8:
+            kmax = max(H, self.Hq * self.D, self.I)
+            self.xq = e(T * kmax, dt=ops.FP8)          # flat; viewed [T, K] per projection
+            self.xs = e(T, dt=torch.float32)
         self.x_last = e(self.max_seqs, H)
         self.logits = e(self.max_seqs, self.v_local, dt=torch.float32)
         self.out_ids = torch.zeros(self.max_seqs, dtype=torch.int32, device=dev)
@@ -140,9 +145,27 @@ class ModelRunner:
         self.v_cache = [torch.zeros(shape, dtype=BF16, device=self.device) for _ in range(self.mcfg.num_hidden_layers)]
 
     # ------------------------------------------------------------------------------ layers
-    def _row_parallel(self, x: torch.Tensor, w: torch.Tensor, T: int, norm_w: torch.Tensor):
+    def _quant(self, x: torch.Tensor, T: int):
+        """bf16 activations -> (e4m3 [T,K], per-token scales [T]) in the shared fp8 staging buffer."""
+        K = x.shape[1]
+        self.stats["kernel_launches"] += 1
+        return ops.quant_fp8_per_token(x, out=self.xq[:T * K].view(T, K), scales=self.xs[:T])
+
+    def _row_parallel(self, x: torch.Tensor, w: torch.Tensor, T: int, norm_w: torch.Tensor,
+                      w_scale: Optional[torch.Tensor] = None):
         """O / down projection followed by (all-reduce +) residual add + RMSNorm -> self.xn."""
         eps = self.mcfg.rms_norm_eps
+        if w_scale is not None:
+            # W8A8: quantise the activations per token, dequantise in the GEMM epilogue
+            xq, xs = self._quant(x, T)
+
+            def mm(out):
+                return ops.gemm_fp8(xq, xs, w, w_scale, out=out)
+            splitk = False
+        else:
+            def mm(out):
+                return ops.gemm(x, w, out=out)
+            splitk = True
         if self.tp > 1:
             ar = self.oneshot
             # one-shot moves (tp-1) x the message over NVLink: right for decode-sized messages only
@@ -151,23 +174,23 @@ class ModelRunner:
                 # every rank's partial over NVLink, sums, adds the residual and normalises.
                 which = self._ar_toggle
                 self._ar_toggle ^= 1
-                ops.gemm(x, w, out=ar.stage(which, T))
+                mm(ar.stage(which, T))
                 ar.allreduce_add_rms_norm(which, self.resid[:T], norm_w, self.xn[:T], self.resid[:T], T, eps)
                 self.stats["kernel_launches"] += 2
                 return
-            ops.gemm(x, w, out=self.hbuf[:T])
+            mm(self.hbuf[:T])
             torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
             ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
                                    residual_out=self.resid[:T])
             self.stats["kernel_launches"] += 3
             return
-        splits = ops.gemm_suggest_splits(T, w.shape[0], w.shape[1]) if T <= _SPLITK_MAX_M else 1
+        splits = ops.gemm_suggest_splits(T, w.shape[0], w.shape[1]) if (splitk and T <= _SPLITK_MAX_M) else 1
         if splits > 1:
             parts = self.partials[:splits * T * self.H].view(splits, T, self.H)
             ops.gemm(x, w, out=parts, splits=splits)
             ops.fused_add_rms_norm_partials(parts, self.resid[:T], norm_w, eps, self.xn[:T], self.resid[:T])
         else:
-            ops.gemm(x, w, out=self.hbuf[:T])
+            mm(self.hbuf[:T])
             ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
                                    residual_out=self.resid[:T])
         self.stats["kernel_launches"] += 2
@@ -180,6 +203,9 @@ class ModelRunner:
         ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
         self.stats["kernel_launches"] += 2   # embedding (by the caller) + this norm
         for l, lw in enumerate(w.layers):
+            if self.fp8:
+                self._layer_fp8(T, l, lw, attn_fn)
+                continue
             qs = ops.gemm_suggest_splits(T, lw.qkv.shape[0], lw.qkv.shape[1]) if T <= _SPLITK_MAX_M else 1
             if qs > 1 or lw.qkv_bias is not None:
                 # fp32 (split-K) partials are reduced -- and the Qwen2 QKV bias added, one rounding --
@@ -198,6 +224,32 @@ class ModelRunner:
             nxt = w.layers[l + 1].input_norm if l + 1 < len(w.layers) else w.final_norm
             self._row_parallel(self.act[:T], lw.down, T, nxt)
             self.stats["kernel_launches"] += 4
+
+    def _layer_fp8(self, T: int, l: int, lw, attn_fn) -> None:
+        """One decoder layer with W8A8 linears (Fp8LinearMethod.apply,
+        $VLLM/model_executor/layers/quantization/fp8.py:437-470): every projection input is
+        quantised per token, the e4m3 GEMM dequantises in its epilogue; norms, RoPE, attention and
+        the residual stream stay bf16 exactly as in the bf16 path."""
+        w = self.w
+        pos, slots = self._pos, self._slots
+        xq, xs = self._quant(self.xn[:T], T)
+        if lw.qkv_bias is not None:
+            # fp32 result + Qwen2 bias folded (one rounding) into the RoPE + KV-write kernel
+            parts = self.partials[:T * self.qkv_width].view(1, T, self.qkv_width)
+            ops.gemm_fp8(xq, xs, lw.qkv, lw.qkv_scale, out=parts[0], out_dtype=torch.float32)
+            ops.rope_kv_write_partials(parts, self.qkv[:T], pos, self.cos_sin, self.k_cache[l], self.v_cache[l],
+                                       slots, self.Hq, self.Hkv, self.D, bias=lw.qkv_bias)
+        else:
+            ops.gemm_fp8(xq, xs, lw.qkv, lw.qkv_scale, out=self.qkv[:T])
+            ops.rope_kv_write(self.qkv[:T], pos, self.cos_sin, self.k_cache[l], self.v_cache[l], slots,
+                              self.Hq, self.Hkv, self.D)
+        attn_fn(l)
+        self._row_parallel(self.attn_out[:T], lw.o, T, lw.post_norm, w_scale=lw.o_scale)
+        xq, xs = self._quant(self.xn[:T], T)
+        ops.gemm_fp8(xq, xs, lw.gate_up, lw.gate_up_scale, out=self.act[:T], silu_mul=True)
+        nxt = w.layers[l + 1].input_norm if l + 1 < len(w.layers) else w.final_norm
+        self._row_parallel(self.act[:T], lw.down, T, nxt, w_scale=lw.down_scale)
+        self.stats["kernel_launches"] += 4
 
     def _sample(self, n: int, rows: Optional[torch.Tensor]) -> None:
         """greedy token of n sequences into self.out_ids[:n]; rows = last-token row of each."""

@@ -1,9 +1,18 @@
-"""Weight loading: HF-format safetensors directory -> fused, tensor-parallel-sharded bf16 tensors.
+"""Weight loading: HF-format safetensors directory -> fused, tensor-parallel-sharded bf16 (or
+fp8 W8A8) tensors.
 
 Sharding follows the reference engine's Megatron layout (SURVEY.md section 8e;
 $VLLM/model_executor/models/llama.py:81-347): QKV and gate_up are column-parallel (each rank owns
 Hq/t query heads, Hkv/t kv heads and I/t MLP columns), O and down are row-parallel (in-dim / t),
 lm_head is vocab-parallel, the embedding table and the norms are replicated.
+
+fp8 (`--quantization fp8`, or a checkpoint whose config.json carries quantization_config
+{quant_method: fp8, activation_scheme: dynamic}): the four decoder linears of every layer are held
+as e4m3 with ONE fp32 scale per fused weight, exactly as the reference engine prepares them --
+bf16 checkpoints are quantised per tensor after fusing and sharding
+($VLLM/model_executor/layers/quantization/fp8.py:537-549), per-tensor fp8 checkpoints are
+re-quantised to the largest shard scale of a fused weight (fp8.py:406-428,
+requantize_with_max_scale).  Embedding, norms and lm_head stay bf16.
 """
 from __future__ import annotations
 
@@ -17,6 +26,9 @@ import torch
 from .config import ModelConfig
 
 BF16 = torch.bfloat16
+FP8 = torch.float8_e4m3fn
+FP8_MAX = 448.0
+FP8_MIN_SCALE = 1.0 / (448.0 * 512.0)
 
 
 @dataclass
@@ -28,6 +40,11 @@ class LayerWeights:
     post_norm: torch.Tensor       # [H]
     gate_up: torch.Tensor         # [2I/t, H]  rows interleaved: 2i = gate_i, 2i+1 = up_i (fused SiLU*mul epilogue)
     down: torch.Tensor            # [H, I/t]
+    # fp8 mode: the four matrices above are float8_e4m3fn and these hold their fp32 scales ([1])
+    qkv_scale: Optional[torch.Tensor] = None
+    o_scale: Optional[torch.Tensor] = None
+    gate_up_scale: Optional[torch.Tensor] = None
+    down_scale: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -50,36 +67,88 @@ def check_tp(cfg: ModelConfig, tp: int) -> None:
         raise ValueError(f"intermediate_size {cfg.intermediate_size} not divisible by 64*tp")
 
 
+def quantize_fp8_per_tensor(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
+    """(e4m3 weight, fp32 scale[1]); scale = max(absmax/448, 1/(448*512)) unless given.  Load-time
+    torch ops on the weight's device (same arithmetic as ops.scaled_fp8_quant(w, scale=None))."""
+    wf = w.to(torch.float32)
+    if scale is None:
+        scale = (wf.abs().max() / FP8_MAX).clamp(min=FP8_MIN_SCALE)
+    scale = scale.to(torch.float32).reshape(1)
+    q = (wf * scale.reciprocal()).clamp(-FP8_MAX, FP8_MAX).to(FP8)
+    return q.contiguous(), scale
+
+
 def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank: int, tp: int,
-                     device: str) -> ModelWeights:
-    """`get(name)` returns the full HF tensor (any device); the result lives on `device`."""
+                     device: str, quantization: Optional[str] = None,
+                     has: Optional[Callable[[str], bool]] = None) -> ModelWeights:
+    """`get(name)` returns the full HF tensor (any device); the result lives on `device`.
+    quantization: None (bf16) or "fp8"; `has(name)` tells whether the checkpoint holds a tensor
+    (needed to find `<proj>.weight_scale` / `.input_scale` of fp8 checkpoints)."""
     check_tp(cfg, tp)
+    if quantization not in (None, "fp8"):
+        raise ValueError(f"unsupported quantization {quantization!r} (supported: fp8)")
     D = cfg.head_dim
     hq, hkv, I = cfg.num_attention_heads // tp, cfg.num_key_value_heads // tp, cfg.intermediate_size // tp
+    fp8 = quantization == "fp8"
 
     def dev(t):
         return t.to(device=device, dtype=BF16).contiguous()
 
+    def shard_scale(name: str) -> Optional[torch.Tensor]:
+        """per-tensor weight_scale of an fp8 checkpoint tensor, None for a bf16 one."""
+        sname = name[: -len("weight")] + "weight_scale"
+        if has is None or not has(sname):
+            return None
+        if has(name[: -len("weight")] + "input_scale"):
+            raise ValueError("fp8 checkpoints with static activation scales are not supported "
+                             "(activation_scheme must be dynamic)")
+        sc = get(sname).to(torch.float32)
+        if sc.numel() != 1:
+            raise ValueError(f"{sname}: only per-tensor fp8 weight scales are supported")
+        return sc.reshape(1).to(device)
+
+    def fuse(names, slicers, interleave: bool = False):
+        """Fused weight of this rank from the checkpoint tensors `names`, each cut by its slicer.
+        bf16 mode -> (bf16 tensor, None); fp8 mode -> (e4m3 tensor, fp32 scale[1])."""
+        parts = [sl(get(n)).to(device) for n, sl in zip(names, slicers)]
+        scales = [shard_scale(n) for n in names] if fp8 else [None] * len(names)
+
+        def merge(ts):
+            if interleave:
+                return torch.stack(ts, dim=1).reshape(2 * ts[0].shape[0], -1)
+            return torch.cat(ts, dim=0) if len(ts) > 1 else ts[0]
+
+        if not fp8:
+            return dev(merge(parts)), None
+        if all(sc is None for sc in scales):                      # online quantisation of a bf16 checkpoint
+            return quantize_fp8_per_tensor(merge([p.to(BF16) for p in parts]))
+        if any(sc is None for sc in scales) or any(p.dtype != FP8 for p in parts):
+            raise ValueError(f"{names}: mixed fp8 / bf16 shards in one fused weight")
+        if len(parts) == 1:
+            return parts[0].contiguous(), scales[0]
+        smax = torch.stack(scales).max().reshape(1)                # requantize_with_max_scale
+        return quantize_fp8_per_tensor(merge([p.to(torch.float32) * sc for p, sc in zip(parts, scales)]), smax)
+
     layers = []
     for l in range(cfg.num_hidden_layers):
         p = f"model.layers.{l}."
-        q = get(p + "self_attn.q_proj.weight")[rank * hq * D:(rank + 1) * hq * D]
-        k = get(p + "self_attn.k_proj.weight")[rank * hkv * D:(rank + 1) * hkv * D]
-        v = get(p + "self_attn.v_proj.weight")[rank * hkv * D:(rank + 1) * hkv * D]
+        qsl = lambda t: t[rank * hq * D:(rank + 1) * hq * D]          # noqa: E731
+        ksl = lambda t: t[rank * hkv * D:(rank + 1) * hkv * D]        # noqa: E731
+        isl = lambda t: t[rank * I:(rank + 1) * I]                    # noqa: E731
         bias = None
         if cfg.attention_bias:
-            bias = dev(torch.cat([get(p + "self_attn.q_proj.bias")[rank * hq * D:(rank + 1) * hq * D],
-                                  get(p + "self_attn.k_proj.bias")[rank * hkv * D:(rank + 1) * hkv * D],
-                                  get(p + "self_attn.v_proj.bias")[rank * hkv * D:(rank + 1) * hkv * D]]))
-        g = get(p + "mlp.gate_proj.weight")[rank * I:(rank + 1) * I]
-        u = get(p + "mlp.up_proj.weight")[rank * I:(rank + 1) * I]
+            bias = dev(torch.cat([qsl(get(p + "self_attn.q_proj.bias")), ksl(get(p + "self_attn.k_proj.bias")),
+                                  ksl(get(p + "self_attn.v_proj.bias"))]))
+        qkv_w, qkv_s = fuse([p + f"self_attn.{n}_proj.weight" for n in "qkv"], [qsl, ksl, ksl])
+        o_w, o_s = fuse([p + "self_attn.o_proj.weight"], [lambda t: t[:, rank * hq * D:(rank + 1) * hq * D]])
+        gu_w, gu_s = fuse([p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight"], [isl, isl], interleave=True)
+        down_w, down_s = fuse([p + "mlp.down_proj.weight"], [lambda t: t[:, rank * I:(rank + 1) * I]])
         layers.append(LayerWeights(
             input_norm=dev(get(p + "input_layernorm.weight")),
-            qkv=dev(torch.cat([q, k, v], dim=0)), qkv_bias=bias,
-            o=dev(get(p + "self_attn.o_proj.weight")[:, rank * hq * D:(rank + 1) * hq * D]),
+            qkv=qkv_w, qkv_bias=bias, o=o_w,
             post_norm=dev(get(p + "post_attention_layernorm.weight")),
-            gate_up=dev(torch.stack([g, u], dim=1).reshape(2 * I, -1)),
-            down=dev(get(p + "mlp.down_proj.weight")[:, rank * I:(rank + 1) * I])))
+            gate_up=gu_w, down=down_w,
+            qkv_scale=qkv_s, o_scale=o_s, gate_up_scale=gu_s, down_scale=down_s))
     embed = dev(get("model.embed_tokens.weight"))
     V = cfg.vocab_size
     per = (V + tp - 1) // tp
@@ -90,7 +159,8 @@ def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank:
                         lm_head=lm, vocab_start=v0, vocab_end=v1)
 
 
-def load_safetensors_dir(cfg: ModelConfig, model_path: str, rank: int, tp: int, device: str) -> ModelWeights:
+def load_safetensors_dir(cfg: ModelConfig, model_path: str, rank: int, tp: int, device: str,
+                         quantization: Optional[str] = None) -> ModelWeights:
     from safetensors import safe_open
 
     root = Path(model_path)
@@ -113,7 +183,8 @@ def load_safetensors_dir(cfg: ModelConfig, model_path: str, rank: int, tp: int, 
             handles[fname] = safe_open(str(root / fname), framework="pt")
         return handles[fname].get_tensor(name)
 
-    return shard_state_dict(cfg, get, rank, tp, device)
+    return shard_state_dict(cfg, get, rank, tp, device, quantization=quantization,
+                            has=lambda name: name in weight_map)
 
 
 def random_state_dict(cfg: ModelConfig, seed: int = 0, std: float = 0.02, device: str = "cuda") -> Dict[str, torch.Tensor]:

@@ -106,6 +106,22 @@ int b200_gemm_pick_block_x(int M, int N, int K);
  * b200_gemm_bf16 followed by b200_silu_and_mul. */
 int b200_gemm_bf16_silu_mul(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx,
                             int64_t ldw, int64_t ldy, void* stream);
+/* W8A8 fp8 (e4m3) projection -- the linear layers of the fp8 checkpoints GPUStack deploys
+ * (BASELINE config "Llama-3-70B fp8"; reference operator: cutlass_scaled_mm behind
+ * Fp8LinearMethod.apply, $VLLM/model_executor/layers/quantization/fp8.py:437-470):
+ *   Y[m,n] = (sum_k Xq[m,k] * Wq[n,k]) * xscale[m] * wscale[n * wscale_stride]
+ * Xq [M,K], Wq [N,K] e4m3 bytes (K-major, K % 128 == 0, N > 128); xscale [M] fp32 dynamic
+ * per-token scales (b200_quant_fp8_per_token); wscale fp32, stride 0 = per-tensor, 1 = per output
+ * channel.  out_f32/splits as b200_gemm_bf16.  silu_mul != 0: W rows are interleaved gate/up and
+ * Y [M, N/2] bf16 gets SiLU*mul of the dequantised, bf16-rounded pair (as b200_gemm_bf16_silu_mul). */
+int b200_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, int K, int64_t ldx, int64_t ldw,
+                  int64_t ldy, const float* xscale, const float* wscale, int wscale_stride, int out_f32,
+                  int splits, int silu_mul, void* stream);
+/* Dynamic per-token e4m3 quantisation of bf16 activations (QuantFP8.forward_native,
+ * $VLLM/model_executor/layers/quantization/input_quant_fp8.py:188-235):
+ *   scales[t] = max(absmax(x[t,:]) / 448, 1/(448*512));  q[t,k] = e4m3(x[t,k] * (1/scales[t])), RNE, saturating. */
+int b200_quant_fp8_per_token(const void* x, int64_t ldx, void* q, int64_t ldq, float* scales, int T, int K,
+                             void* stream);
 /* Y[m,n] = bf16(sum_s partials[s][m][n]). */
 int b200_splitk_reduce(const float* partials, int splits, void* Y, int M, int N, int64_t ldy,
                        void* stream);

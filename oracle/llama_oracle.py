@@ -86,6 +86,36 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -
     return y.to(x.dtype)
 
 
+# ------------------------------------------------------------------------------- fp8 (W8A8)
+FP8 = torch.float8_e4m3fn
+FP8_MAX = 448.0
+FP8_MIN_SCALE = 1.0 / (448.0 * 512.0)
+
+
+def quant_fp8(x: torch.Tensor, per_token: bool = True):
+    """$VLLM/model_executor/layers/quantization/input_quant_fp8.py:188-235 (QuantFP8.forward_native,
+    dynamic): scale = max(absmax / 448, 1/(448*512)) per token row (activations) or over the whole
+    tensor (online weight quantisation, fp8.py:537-549); q = e4m3(clamp(float(x) * (1/scale)))."""
+    if per_token:
+        amax = x.abs().max(dim=-1, keepdim=True)[0].to(torch.float32)
+    else:
+        amax = x.abs().max().to(torch.float32).reshape(1)
+    scale = (amax / FP8_MAX).clamp(min=FP8_MIN_SCALE)
+    q = (x.to(torch.float32) * scale.reciprocal()).clamp(-FP8_MAX, FP8_MAX).to(FP8)
+    return q, scale
+
+
+def fp8_linear(x: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fp8LinearMethod.apply -> cutlass_scaled_mm ($VLLM/.../quantization/fp8.py:437-470): dynamic
+    per-token activation scales, e4m3 x e4m3 products accumulated in fp32, multiplied by both
+    scales (+ bias) in fp32, one rounding to bf16.  `wq` may be e4m3 or its exact fp32 image."""
+    xq, xs = quant_fp8(x, per_token=True)
+    y = (xq.to(torch.float32) @ wq.to(torch.float32).t()) * xs * w_scale.to(torch.float32)
+    if b is not None:
+        y = y + b.to(torch.float32)
+    return y.to(x.dtype)
+
+
 def attention_ref(q, k, v, scale: float, q_pos: torch.Tensor) -> torch.Tensor:
     """Causal GQA attention over a contiguous K/V history.
     q [Tq, Hq, D], k/v [Tk, Hkv, D]; query i may see keys 0..q_pos[i].  fp32 softmax.
@@ -190,11 +220,31 @@ class OracleLlama:
     ($VLLM/model_executor/models/llama.py:316-333, 395-434) with a plain contiguous KV history per
     sequence.  bf16 tensors between operators, fp32 inside them."""
 
-    def __init__(self, cfg: LlamaConfig, weights: Dict[str, torch.Tensor], fp32_cache: bool = False):
+    def __init__(self, cfg: LlamaConfig, weights: Dict[str, torch.Tensor], fp32_cache: bool = False,
+                 quantization: Optional[str] = None):
         """fp32_cache=True keeps an fp32 copy of every matmul weight (same arithmetic, no per-call
-        upcast) -- used when this oracle is timed as the CPU baseline."""
+        upcast) -- used when this oracle is timed as the CPU baseline.
+        quantization="fp8": the decoder linears run W8A8 as the reference engine's online fp8 mode
+        does (`--quantization fp8`): each MERGED weight (qkv, gate_up) and o / down gets one
+        per-tensor scale (fp8.py:537-549), activations per-token dynamic scales; lm_head stays bf16."""
         self.cfg = cfg
         self.w = {k: v.to("cpu") for k, v in weights.items()}
+        self.q8: Dict[str, tuple] = {}
+        if quantization == "fp8":
+            for l in range(cfg.num_hidden_layers):
+                p = f"model.layers.{l}."
+                for group in (("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"), ("self_attn.o_proj",),
+                              ("mlp.gate_proj", "mlp.up_proj"), ("mlp.down_proj",)):
+                    names = [p + g + ".weight" for g in group]
+                    merged = torch.cat([self.w[n] for n in names], dim=0)
+                    mq, ms = quant_fp8(merged, per_token=False)
+                    r0 = 0
+                    for n in names:
+                        rows = self.w[n].shape[0]
+                        self.q8[n] = (mq[r0:r0 + rows].to(torch.float32), ms)
+                        r0 += rows
+        elif quantization is not None:
+            raise ValueError(f"unsupported quantization {quantization!r}")
         self.wf = {k: v.to(torch.float32) for k, v in self.w.items() if v.dim() == 2 and "embed" not in k} \
             if fp32_cache else {}
         self.cache = cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta)
@@ -243,6 +293,8 @@ class OracleLlama:
     def _lin(self, x: torch.Tensor, name: str) -> torch.Tensor:
         wf = self.wf.get(name)
         b = self.w.get(name.replace(".weight", ".bias"))
+        if name in self.q8:
+            return fp8_linear(x, self.q8[name][0], self.q8[name][1], b)
         if wf is None:
             return linear(x, self.w[name], b)
         y = x.to(torch.float32) @ wf.t()

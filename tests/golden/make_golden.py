@@ -7,7 +7,7 @@ Sources of truth imported here (never at test time on the GPU box):
     fused_add_rms_norm}, RotaryEmbedding.forward_static (neox), SiluAndMul.forward_native;
   * HF transformers LlamaForCausalLM (eager attention) for whole-model logits and greedy tokens
     of the seeded tiny Llama configs.
-Outputs: tests/golden/ops_vllm.pt, tests/golden/tiny_llama_hf.pt (a few hundred KB).
+Outputs: tests/golden/ops_vllm.pt, fp8_quant_vllm.pt, tiny_llama_hf.pt, tiny_qwen2_hf.pt (a few hundred KB).
 """
 import sys
 from pathlib import Path
@@ -54,6 +54,30 @@ def ops_from_vllm():
     out["silu_y"] = SiluAndMul.forward_native(xs)
     torch.save(out, OUT / "ops_vllm.pt")
     print("wrote ops_vllm.pt")
+
+
+def fp8_quant_from_vllm():
+    """Dynamic fp8 quantisation as the reference engine's W8A8 linears apply it (QuantFP8.forward_native;
+    the module needs a vLLM config context to be constructed, the method itself only reads four
+    attributes, so it is called on a plain namespace)."""
+    from types import SimpleNamespace
+
+    from vllm.model_executor.layers.quantization.input_quant_fp8 import QuantFP8
+    from vllm.model_executor.layers.quantization.utils.quant_utils import GroupShape
+
+    g = torch.Generator().manual_seed(4321)
+    x = (torch.randn(7, 384, generator=g) * 2.5).to(BF)
+    x[2] = 0                                   # all-zero row -> minimum scale
+    x[3, 5] = 3000.0                           # outlier: the rest of the row collapses towards 0
+    x[4] = x[4] * 1e-4
+    out = {"x": x}
+    for key, shape in (("token", GroupShape.PER_TOKEN), ("tensor", GroupShape.PER_TENSOR)):
+        ns = SimpleNamespace(static=False, group_shape=shape, is_group_quant=False, num_token_padding=None)
+        q, scale = QuantFP8.forward_native(ns, x)
+        out[f"q_{key}"] = q.view(torch.uint8).clone()
+        out[f"scale_{key}"] = scale.clone()
+    torch.save(out, OUT / "fp8_quant_vllm.pt")
+    print("wrote fp8_quant_vllm.pt")
 
 
 def tiny_llama_from_hf():
@@ -115,5 +139,6 @@ def tiny_qwen2_from_hf():
 
 if __name__ == "__main__":
     ops_from_vllm()
+    fp8_quant_from_vllm()
     tiny_llama_from_hf()
     tiny_qwen2_from_hf()

@@ -26,7 +26,7 @@ def _engine(cfg_o, seed=7, **kw):
     ecfg = EngineConfig(max_num_seqs=kw.pop("max_num_seqs", 16), max_num_batched_tokens=kw.pop("mbt", 256),
                         num_gpu_blocks=kw.pop("blocks", 128), **kw)
     eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
-    return eng, O.OracleLlama(cfg_o, weights)
+    return eng, O.OracleLlama(cfg_o, weights, quantization=ecfg.quantization)
 
 
 @pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128, O.TINY_QWEN2], ids=["tiny64", "tiny128", "qwen2-bias-tied-g7"])
@@ -143,3 +143,41 @@ def test_prefix_caching_matches_uncached_run():
         agree = sum(x == y for x, y in zip(a, b)) / len(a)
         assert agree >= 0.9 or a[: len(a) // 2] == b[: len(b) // 2]
     assert eng.sched.pool.num_free == eng.sched.pool.num_total
+
+
+@pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128, O.TINY_QWEN2], ids=["tiny64", "tiny128", "qwen2-bias-tied-g7"])
+def test_fp8_w8a8_engine_matches_fp8_oracle(cfg_o):
+    """`--quantization fp8`: per-tensor e4m3 weights of the fused projections, dynamic per-token
+    e4m3 activations (BASELINE config "Llama-3-70B fp8" at a size the oracle runs in seconds).
+    Stated tolerance: last-position logits max-abs-diff <= 4e-2 * max|logit| against the oracle
+    run in the same W8A8 mode -- twice the bf16 tolerance, because a one-ulp bf16 difference in a
+    projection input can move an activation to the neighbouring e4m3 code (a 6 % step); greedy
+    tokens teacher-forced, exact wherever the oracle's top-2 margin exceeds that tolerance."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    eng, oracle = _engine(cfg_o, enforce_eager=True, quantization="fp8")
+    assert eng.runner.fp8 and eng.runner.w.layers[0].qkv.dtype == torch.float8_e4m3fn
+    g = torch.Generator().manual_seed(13)
+    prompts = [torch.randint(3, cfg_o.vocab_size, (n,), generator=g).tolist() for n in (9, 40, 70)]
+    eng.add_request("p0", prompts[1], SamplingParams(max_tokens=1, ignore_eos=True))
+    eng.step()
+    got = eng.runner.last_logits(1)[0].cpu()
+    ref = oracle.forward(0, prompts[1])[-1]
+    tol = 4e-2 * float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= tol
+    # the W8A8 engine must be closer to the W8A8 oracle than the bf16 oracle is
+    bf16_ref = O.OracleLlama(cfg_o, O.init_weights(cfg_o, seed=7)).forward(0, prompts[1])[-1]
+    assert float((got - ref).abs().max()) < float((bf16_ref - ref).abs().max())
+    N = 16
+    outs = eng.generate(prompts, SamplingParams(max_tokens=N, ignore_eos=True))
+    n_checked = 0
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        oracle.reset()
+        logits = oracle.forward(i, p)[-1]
+        for t in range(N):
+            top2 = torch.topk(logits, 2).values
+            if float(top2[0] - top2[1]) > 4e-2 * float(logits.abs().max()):
+                assert int(torch.argmax(logits)) == o[t], f"seq {i} step {t}"
+                n_checked += 1
+            logits = oracle.forward(i, [o[t]])[-1]
+    assert n_checked >= N // 2

@@ -228,6 +228,96 @@ def test_gemm_silu_mul_fused_equals_unfused(ops, M, I, K, out_dir):
         _close(fused, ref, 2e-2, 3.2e-2, f"gemm_silu_mul {M}x{I}x{K}", out_dir)
 
 
+# ------------------------------------------------------------------------------- fp8 (W8A8)
+@pytest.mark.parametrize("T,K", [(1, 4096), (7, 896), (300, 14336), (33, 512), (5, 28672)])
+def test_quant_fp8_per_token_is_bit_exact(ops, T, K):
+    """bytes and scales equal the oracle's (= vLLM QuantFP8.forward_native, pinned by
+    tests/golden/fp8_quant_vllm.pt); includes an all-zero row, an outlier row and a tiny row."""
+    g = torch.Generator().manual_seed(T + K)
+    x = (torch.randn(T, K, generator=g) * 2.0).to(BF)
+    if T > 4:
+        x[1] = 0
+        x[2, 3] = 3000.0
+        x[3] = x[3] * 1e-4
+    q, s = ops.quant_fp8_per_token(x.cuda())
+    rq, rs = O.quant_fp8(x, per_token=True)
+    assert torch.equal(s.cpu(), rs.reshape(-1))
+    assert torch.equal(q.cpu().view(torch.uint8), rq.view(torch.uint8))
+    # strided input (a column slice) and a wider output buffer
+    big = (torch.randn(T, K + 64, generator=g)).to(BF).cuda()
+    q2, s2 = ops.quant_fp8_per_token(big[:, 64:])
+    rq2, rs2 = O.quant_fp8(big[:, 64:].cpu(), per_token=True)
+    assert torch.equal(s2.cpu(), rs2.reshape(-1)) and torch.equal(q2.cpu().view(torch.uint8), rq2.view(torch.uint8))
+
+
+FP8_GEMM_SHAPES = [
+    # M, N, K, splits, f32, per_channel
+    (1, 256, 128, 1, 0, 0), (5, 384, 512, 1, 0, 0), (16, 6144, 4096, 1, 0, 0), (33, 4096, 4096, 1, 0, 1),
+    (64, 4096, 14336, 1, 0, 0), (100, 28672, 4096, 1, 0, 0), (128, 4096, 4096, 1, 0, 0),
+    (256, 6144, 4096, 1, 0, 0), (200, 1000, 896, 1, 0, 1),           # M / N tails
+    (512, 6144, 4096, 1, 0, 0), (1000, 4096, 4096, 1, 0, 0), (2048, 4096, 14336, 1, 0, 0),
+    (8, 1280, 8192, 1, 1, 0),                                        # fp32 output (QKV + bias path)
+    (64, 4096, 14336, 4, 1, 0), (7, 4096, 4096, 8, 1, 1),            # split-K partials
+]
+
+
+@pytest.mark.parametrize("M,N,K,splits,f32,per_channel", FP8_GEMM_SHAPES)
+def test_gemm_fp8(ops, M, N, K, splits, f32, per_channel, out_dir):
+    """e4m3 x e4m3 tcgen05 GEMM with the dequantising epilogue == exact fp64 product of the same
+    quantised operands times the scales (the only slack is fp32 accumulation order + one bf16
+    rounding; same tolerances as the bf16 GEMM test)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N + K)
+    x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(BF)
+    xq, xs = ops.quant_fp8_per_token(x)
+    if per_channel:
+        ws = (w.float().abs().amax(dim=1) / 448.0).clamp(min=1e-8)
+        wq = (w.float() / ws[:, None]).clamp(-448, 448).to(torch.float8_e4m3fn)
+    else:
+        ws = (w.float().abs().max() / 448.0).reshape(1)
+        wq = (w.float() / ws).clamp(-448, 448).to(torch.float8_e4m3fn)
+    ref = (xq.double() @ wq.double().t()) * xs.double()[:, None] * ws.double()[None, :]
+    scale = 0.02 * math.sqrt(K)
+    if splits > 1:
+        parts = ops.gemm_fp8(xq, xs, wq, ws, splits=splits)
+        assert parts.shape == (splits, M, N) and parts.dtype == torch.float32
+        _close(parts.double().sum(0), ref, 2e-3 * scale, 2e-3, f"gemm_fp8 splitK {M}x{N}x{K}/{splits}", out_dir)
+    elif f32:
+        y = ops.gemm_fp8(xq, xs, wq, ws, out_dtype=torch.float32)
+        _close(y, ref, 2e-3 * scale, 2e-3, f"gemm_fp8 f32 {M}x{N}x{K}", out_dir)
+    else:
+        y = ops.gemm_fp8(xq, xs, wq, ws)
+        _close(y, ref, 1e-2 * scale, 1.6e-2, f"gemm_fp8 {M}x{N}x{K}", out_dir)
+        # and it tracks the unquantised bf16 product to fp8 accuracy
+        full = x.double() @ w.double().t()
+        assert float((y.double() - full).abs().max()) <= 0.15 * float(full.abs().max())
+
+
+@pytest.mark.parametrize("M,I,K", [(1, 256, 128), (7, 1024, 512), (64, 14336, 4096), (256, 14336, 4096),
+                                   (1000, 3584, 8192)])
+def test_gemm_fp8_silu_mul_fused_equals_unfused(ops, M, I, K, out_dir):
+    g = torch.Generator(device="cuda").manual_seed(M + I + 1)
+    x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+    wg = (torch.randn(I, K, generator=g, device="cuda") * 0.03).to(BF)
+    wu = (torch.randn(I, K, generator=g, device="cuda") * 0.03).to(BF)
+    xq, xs = ops.quant_fp8_per_token(x)
+    ws = (torch.cat([wg, wu]).float().abs().max() / 448.0).reshape(1)
+    q = lambda t: (t.float() / ws).clamp(-448, 448).to(torch.float8_e4m3fn)      # noqa: E731
+    fused = ops.gemm_fp8(xq, xs, ops.interleave_gate_up(q(wg).view(torch.uint8), q(wu).view(torch.uint8))
+                         .view(torch.float8_e4m3fn), ws, silu_mul=True)
+    unfused = ops.silu_and_mul(ops.gemm_fp8(xq, xs, torch.cat([q(wg), q(wu)], dim=0).contiguous(), ws))
+    assert fused.shape == (M, I) and torch.equal(fused, unfused)
+
+
+def test_gemm_fp8_vs_cpu_oracle(ops, out_dir):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(40, 512, generator=g).to(BF); w = (torch.randn(640, 512, generator=g) * 0.05).to(BF)
+    wq, ws = O.quant_fp8(w, per_token=False)
+    xq, xs = ops.quant_fp8_per_token(x.cuda())
+    y = ops.gemm_fp8(xq, xs, wq.cuda(), ws.cuda())
+    _close(y, O.fp8_linear(x, wq, ws), 1e-2, 1.6e-2, "gemm_fp8 vs oracle.fp8_linear", out_dir)
+
+
 def test_gemm_vs_cpu_oracle(ops, out_dir):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(40, 512, generator=g).to(BF); w = (torch.randn(640, 512, generator=g) * 0.05).to(BF)

@@ -95,3 +95,34 @@ def test_qwen2_family_against_hf():
     agree = [a == b for a, b in zip(g["greedy_fp32"], g["greedy_bf16"])]
     n_stable = agree.index(False) if False in agree else len(agree)
     assert mine[:n_stable] == g["greedy_fp32"][:n_stable]
+
+
+def test_fp8_quant_against_vllm_native():
+    """oracle.quant_fp8 == vLLM's QuantFP8.forward_native bit for bit (dynamic per-token and
+    per-tensor), including the all-zero row (minimum scale) and the outlier row."""
+    g = torch.load(GOLD / "fp8_quant_vllm.pt", weights_only=False)
+    for key, per_token in (("token", True), ("tensor", False)):
+        q, s = O.quant_fp8(g["x"], per_token=per_token)
+        assert torch.equal(s.reshape(-1), g[f"scale_{key}"].reshape(-1))
+        assert torch.equal(q.view(torch.uint8), g[f"q_{key}"])
+    assert float(g["scale_token"][2]) == float(torch.tensor(1.0 / (448.0 * 512.0), dtype=torch.float32))
+
+
+def test_fp8_linear_is_the_dequantised_product():
+    """fp8_linear == fp32 matmul of the dequantised operands (the definition cutlass_scaled_mm
+    implements), and fp8 model mode stays close to -- but is not -- the bf16 model."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 256, generator=g).to(BF)
+    w = (torch.randn(40, 256, generator=g) * 0.05).to(BF)
+    wq, ws = O.quant_fp8(w, per_token=False)
+    y = O.fp8_linear(x, wq, ws)
+    xq, xs = O.quant_fp8(x)
+    ref = ((xq.float() * xs) @ (wq.float() * ws).t())
+    assert float((y.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+    assert float((y.float() - O.linear(x, w).float()).abs().max()) <= 8e-2 * float(ref.abs().max())
+    wts = O.init_weights(O.TINY, seed=7)
+    p = list(range(5, 40))
+    la = O.OracleLlama(O.TINY, wts).forward(0, p)[-1]
+    lb = O.OracleLlama(O.TINY, wts, quantization="fp8").forward(0, p)[-1]
+    d = float((la - lb).abs().max()) / float(la.abs().max())
+    assert 1e-3 < d < 0.25

@@ -104,3 +104,101 @@ def test_config_parsing_and_byte_accounting():
     b = e.graph_buckets()
     assert b[0] == 1 and b[-1] == 100 and b == sorted(set(b))
     assert tiny_llama(128).head_dim == 128
+
+
+# ---------------------------------------------------------------------------------- fp8 (W8A8)
+def _deq(w, s):
+    return w.to(torch.float32) * s
+
+
+def test_online_fp8_quantisation_matches_the_oracle():
+    """`--quantization fp8` on a bf16 checkpoint: one per-tensor scale per FUSED projection, same
+    bytes as oracle.quant_fp8 of the fused weight (vLLM fp8.py:537-549)."""
+    from oracle import llama_oracle as O
+
+    cfg = _cfg(bias=True)
+    sd = random_state_dict(cfg, seed=4, device="cpu")
+    w = shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu", quantization="fp8", has=lambda k: k in sd)
+    p = "model.layers.0."
+    lw = w.layers[0]
+    assert lw.qkv.dtype == torch.float8_e4m3fn and lw.qkv_scale.shape == (1,) and lw.qkv_bias.dtype == torch.bfloat16
+    fused = torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"])
+    rq, rs = O.quant_fp8(fused, per_token=False)
+    assert torch.equal(lw.qkv.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(lw.qkv_scale, rs)
+    g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+    rq, rs = O.quant_fp8(torch.cat([g, u]), per_token=False)
+    I = cfg.intermediate_size
+    assert torch.equal(lw.gate_up.view(torch.uint8)[0::2], rq.view(torch.uint8)[:I])       # interleaved rows
+    assert torch.equal(lw.gate_up.view(torch.uint8)[1::2], rq.view(torch.uint8)[I:]) and torch.equal(lw.gate_up_scale, rs)
+    for name, t, sc in (("self_attn.o_proj", lw.o, lw.o_scale), ("mlp.down_proj", lw.down, lw.down_scale)):
+        rq, rs = O.quant_fp8(sd[p + name + ".weight"], per_token=False)
+        assert torch.equal(t.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(sc, rs)
+    assert w.embed.dtype == torch.bfloat16 and w.lm_head.dtype == torch.bfloat16 and w.final_norm.dtype == torch.bfloat16
+    # quantisation error of the dequantised weight stays within one e4m3 step (2^-4 relative)
+    err = (_deq(lw.o, lw.o_scale) - sd[p + "self_attn.o_proj.weight"].float()).abs().max()
+    assert float(err) <= float(lw.o_scale) * 448 * 2 ** -4
+
+
+def test_fp8_checkpoint_round_trip_requantises_fused_shards_to_the_max_scale(tmp_path):
+    """A per-tensor fp8 checkpoint (weight + weight_scale per projection, as `--quantization fp8`
+    exports and llm-compressor's FP8_DYNAMIC-per-tensor writes): single projections are taken
+    as they are, fused ones are re-quantised to the largest shard scale (vLLM fp8.py:406-428)."""
+    from oracle import llama_oracle as O
+
+    cfg = _cfg()
+    sd = random_state_dict(cfg, seed=5, device="cpu")
+    q8 = {}
+    for k, v in sd.items():
+        if k.endswith("_proj.weight"):
+            mul = 3.0 if "k_proj" in k else 1.0                    # make the shard scales differ
+            wq, ws = O.quant_fp8((v.float() * mul).to(torch.bfloat16), per_token=False)
+            q8[k] = wq
+            q8[k[: -len("weight")] + "weight_scale"] = ws.reshape(())
+        else:
+            q8[k] = v
+    cfg8 = ModelConfig.from_dict({**cfg.to_hf_dict(), "quantization_config": {"quant_method": "fp8",
+                                                                             "activation_scheme": "dynamic"}})
+    assert cfg8.quantization == "fp8" and cfg8.to_hf_dict()["quantization_config"]["quant_method"] == "fp8"
+    save_checkpoint(cfg8, q8, str(tmp_path / "ckpt8"))
+    cfg_l = ModelConfig.from_pretrained(str(tmp_path / "ckpt8"))
+    assert cfg_l.quantization == "fp8"
+    w = load_safetensors_dir(cfg_l, str(tmp_path / "ckpt8"), 0, 1, "cpu", quantization=cfg_l.quantization)
+    p = "model.layers.1."
+    lw = w.layers[1]
+    assert torch.equal(lw.o.view(torch.uint8), q8[p + "self_attn.o_proj.weight"].view(torch.uint8))
+    assert torch.equal(lw.o_scale, q8[p + "self_attn.o_proj.weight_scale"].reshape(1))
+    scs = [q8[p + f"self_attn.{n}_proj.weight_scale"] for n in "qkv"]
+    assert torch.equal(lw.qkv_scale, torch.stack(scs).max().reshape(1)) and float(scs[1]) > float(scs[0])
+    deq_ref = torch.cat([_deq(q8[p + f"self_attn.{n}_proj.weight"], q8[p + f"self_attn.{n}_proj.weight_scale"])
+                         for n in "qkv"])
+    # the shard that owned the max scale is reproduced exactly, the others within one e4m3 step of the new scale
+    nq = cfg.q_size
+    kk = slice(nq, nq + cfg.kv_size)
+    assert torch.equal(_deq(lw.qkv, lw.qkv_scale)[kk], deq_ref[kk])
+    assert float((_deq(lw.qkv, lw.qkv_scale) - deq_ref).abs().max()) <= float(lw.qkv_scale) * 448 * 2 ** -4
+    # tensor-parallel shards quantise their own slice
+    w2 = load_safetensors_dir(cfg_l, str(tmp_path / "ckpt8"), 1, 2, "cpu", quantization="fp8")
+    assert w2.layers[0].down.shape == (cfg.hidden_size, cfg.intermediate_size // 2)
+    assert w2.layers[0].down.dtype == torch.float8_e4m3fn
+
+
+def test_unsupported_quantisation_configs_are_refused():
+    base = _cfg().to_hf_dict()
+    for qc in ({"quant_method": "awq"}, {"quant_method": "fp8", "activation_scheme": "static"},
+               {"quant_method": "fp8", "weight_block_size": [128, 128]}):
+        with pytest.raises(ValueError):
+            ModelConfig.from_dict({**base, "quantization_config": qc})
+    cfg = _cfg()
+    sd = random_state_dict(cfg, seed=6, device="cpu")
+    with pytest.raises(ValueError):
+        shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu", quantization="int4")
+    # static activation scales in the checkpoint
+    from oracle import llama_oracle as O
+    q8 = dict(sd)
+    for k in list(sd):
+        if k.endswith("_proj.weight"):
+            q8[k], s = O.quant_fp8(sd[k], per_token=False)
+            q8[k[:-6] + "weight_scale"] = s
+            q8[k[:-6] + "input_scale"] = torch.ones(1)
+    with pytest.raises(ValueError, match="static activation"):
+        shard_state_dict(cfg, lambda k: q8[k], 0, 1, "cpu", quantization="fp8", has=lambda k: k in q8)
