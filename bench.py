@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tiny", "tiny128"])
     ap.add_argument("--max-num-batched-tokens", type=int, default=8192, help="prefill token budget per engine step")
+    ap.add_argument("--quantization", default=None, choices=[None, "fp8"],
+                    help="fp8 = W8A8 side measurement (NOT the BASELINE config, which is bf16)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the HTTP end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-requests", type=int, default=2)
@@ -289,6 +291,7 @@ def run_ours(a):
                         max_num_batched_tokens=a.max_num_batched_tokens,
                         max_model_len=min(mcfg.max_position_embeddings, max(1024, a.input_len + a.output_len + 16)),
                         enable_prefix_caching=False,    # every timed token is computed (same as the vLLM baseline run)
+                        quantization=a.quantization,
                         seed=0)
     t_init = time.perf_counter()
     engine = LLMEngine.from_engine_config(ecfg, mcfg=mcfg)
@@ -357,8 +360,8 @@ def run_ours(a):
     res = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
         "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Llama-3-8B bf16 TP={a.gpus}, continuous batching, {a.input_len}-in/{a.output_len}-out greedy"
+        "dtype": "bf16" if a.quantization is None else "fp8 e4m3 W8A8 linears, bf16 elsewhere", "data": "synthetic",
+        "config": {"workload": f"Llama-3-8B {'bf16' if a.quantization is None else 'fp8-W8A8'} TP={a.gpus}, continuous batching, {a.input_len}-in/{a.output_len}-out greedy"
                    if a.model == "llama3-8b" else f"{a.model} TP={a.gpus} {a.input_len}-in/{a.output_len}-out",
                    "requests_per_step": R, "concurrency": R, "weights": "seeded N(0,0.02) random init",
                    "prompts": "seeded uniform token ids, fresh per step (working set 16 GB weights >> 126 MB L2)",

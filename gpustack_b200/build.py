@@ -22,6 +22,7 @@ SOURCES = [
     "elementwise.cu",
     "gemm_tcgen05.cu",
     "quant_fp8.cu",
+    "moe.cu",
     "attention.cu",
     "allreduce.cu",
 ]

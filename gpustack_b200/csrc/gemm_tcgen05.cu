@@ -318,12 +318,24 @@ struct Gemm2Cfg {
 // 128 elements instead of 64, and one MMA consumes 32 bytes of K either way, so the pipeline is
 // byte-for-byte the bf16 one; only the element counts handed to TMA, the instruction kind and the
 // dequantising epilogue differ.
-template <int BLOCK_X, int EPI, int FP8>
+// GROUPED 1: mixture-of-experts grouped GEMM.  The token rows live in a permuted row space in which
+// every m-tile (BLOCK_X rows) belongs to ONE expert (moe.cu: moe_align_kernel); W stacks the
+// experts' [N, K] matrices along its rows, so tile (m, n) multiplies rows of X with weight rows
+// tile_expert[m] * N + n*128...  The number of m-tiles in use is read from device memory after the
+// dependency wait (no host round trip, graph capturable); `xscale`, when given, is the per-row
+// routing weight applied to the fp32 accumulator (MUL_ROUTED_WEIGHT of the reference's fused_moe).
+struct GroupInfo {
+  const int32_t* tile_expert;   // [max m_tiles]
+  const int32_t* num_m_tiles;   // device scalar
+};
+
+template <int BLOCK_X, int EPI, int FP8, int GROUPED = 0>
 __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_x,
                                               void* __restrict__ Yv, int M, int N, int K, int64_t ldy,
                                               int out_f32, int splits, int n_tiles, int m_tiles,
                                               int group_m, const float* __restrict__ xscale,
-                                              const float* __restrict__ wscale, int wscale_stride) {
+                                              const float* __restrict__ wscale, int wscale_stride,
+                                              GroupInfo grp = GroupInfo{nullptr, nullptr}) {
   using Cfg = Gemm2Cfg<BLOCK_X>;
   constexpr int kElemsK = FP8 ? 2 * kBlockK : kBlockK;   // elements per 128-byte k-block
   constexpr int STAGES = Cfg::kStages;
@@ -366,6 +378,10 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
+  if constexpr (GROUPED) {
+    const int used = *grp.num_m_tiles;   // written by the align kernel this grid depends on
+    m_tiles = used < m_tiles ? used : m_tiles;
+  }
   const int kb_per_split = (K / kElemsK) / splits;
   const int n_units = (n_tiles + 1) / 2;  // a unit = a pair of adjacent weight tiles (256 rows)
   const int total_units = n_units * m_tiles * splits;
@@ -381,6 +397,8 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
       for (int u = first_unit; u < total_units; u += unit_stride) {
         const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
         const int n_tile = c.n_tile * 2 + (int)crank;
+        int w_row = n_tile * kBlockW;
+        if constexpr (GROUPED) w_row += grp.tile_expert[c.m_tile] * N;
         const int k0 = c.split * kb_per_split * kElemsK;
         for (int kb = 0; kb < kb_per_split; ++kb) {
           mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
@@ -388,7 +406,7 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
           uint8_t* b = a + Cfg::kABytes;
           // this CTA's bytes are announced on the LEADER's barrier, where the TMAs complete
           mbar_expect_tx_cluster(mapa_u32(&full_bar[stage], 0), Cfg::kStageBytes);
-          tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kElemsK, n_tile * kBlockW, hint_w);
+          tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kElemsK, w_row, hint_w);
           tma_load_2d_2sm(b, &tmap_x, &full_bar[stage], k0 + kb * kElemsK,
                           c.m_tile * BLOCK_X + (int)crank * Cfg::kHalf, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -445,6 +463,9 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
         const float ws = n < N ? wscale[(size_t)n * wscale_stride] : 0.f;
         epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane,
                                              xscale, ws);
+      } else if (GROUPED && xscale != nullptr) {
+        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane,
+                                             xscale, 1.f);
       } else {
         epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
       }
@@ -487,6 +508,18 @@ gemm_fp8_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                             const float* __restrict__ wscale, int wscale_stride) {
   gemm_2sm_body<BLOCK_X, EPI, 1>(tmap_w, tmap_x, Yv, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
                                  group_m, xscale, wscale, wscale_stride);
+}
+
+// Grouped (mixture-of-experts) projection: see GroupInfo above.
+template <int BLOCK_X, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_grouped_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
+                             int N, int K, int64_t ldy, int n_tiles, int m_tiles, int group_m,
+                             const float* __restrict__ row_scale, const int32_t* __restrict__ tile_expert,
+                             const int32_t* __restrict__ num_m_tiles) {
+  gemm_2sm_body<BLOCK_X, EPI, 0, 1>(tmap_w, tmap_x, Yv, M, N, K, ldy, 0, 1, n_tiles, m_tiles, group_m,
+                                    row_scale, nullptr, 0, GroupInfo{tile_expert, num_m_tiles});
 }
 
 static int g_gemm_multicast = -1;  // -1: read B200_GEMM_MULTICAST once (default on)
@@ -789,4 +822,82 @@ extern "C" int b200_gemm_fp8(const void* X, const void* W, void* Y, int M, int N
       B200_FP8_CASE(256)
   }
 #undef B200_FP8_CASE
+}
+
+namespace b200 {
+template <int BLOCK_X, int EPI>
+static int launch_gemm_grouped(const void* X, const void* W, void* Y, int M, int N, int K, int E, int64_t ldx,
+                               int64_t ldw, int64_t ldy, const float* row_scale, const int32_t* tile_expert,
+                               const int32_t* num_m_tiles, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BLOCK_X>;
+  auto kernel = gemm_bf16_grouped_2sm_kernel<BLOCK_X, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      b200_set_error("gemm(grouped): cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return B200_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_tmap_bf16_2d(&tw, W, (uint64_t)E * (uint64_t)N, (uint64_t)K, (uint64_t)ldw, kBlockW, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
+  if (rc) return rc;
+  const int n_tiles = (N + kBlockW - 1) / kBlockW;
+  const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;      // capacity; the kernel clamps to the tiles in use
+  const int total = ((n_tiles + 1) / 2) * m_tiles;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int clusters = total < sms / 2 ? total : sms / 2;
+  const int group_m = gemm_group_m(m_tiles);
+  cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
+                             tw, tx, Y, M, N, K, ldy, n_tiles, m_tiles, group_m, row_scale, tile_expert,
+                             num_m_tiles);
+  if (e != cudaSuccess) {
+    b200_set_error("b200_moe_grouped_gemm: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200_ERR_CUDA;
+  }
+  return b200_check_launch("b200_moe_grouped_gemm");
+}
+}  // namespace b200
+
+// Grouped expert projection over the permuted row space of b200_moe_align (block_x must be the
+// one the rows were aligned to).  X [capacity_rows, K] bf16, W [E*N, K] bf16 (experts stacked),
+// Y [capacity_rows, N] bf16 (or [capacity_rows, N/2] with silu_mul over interleaved gate/up rows);
+// row_scale (optional, fp32 [capacity_rows]) multiplies the fp32 accumulator of each row.
+extern "C" int b200_moe_grouped_gemm(const void* X, const void* W, void* Y, int capacity_rows, int N, int K,
+                                     int num_experts, int64_t ldx, int64_t ldw, int64_t ldy,
+                                     const float* row_scale, const int32_t* tile_expert,
+                                     const int32_t* num_tiles, int block_x, int silu_mul, void* stream) {
+  B200_REQUIRE(capacity_rows > 0 && N > 0 && K > 0 && num_experts >= 1, "moe_grouped_gemm: bad shape");
+  B200_REQUIRE(K % kBlockK == 0, "moe_grouped_gemm: K=%d must be a multiple of %d", K, kBlockK);
+  B200_REQUIRE(N % (2 * kBlockW) == 0, "moe_grouped_gemm: N=%d per expert must be a multiple of %d", N, 2 * kBlockW);
+  B200_REQUIRE(block_x > 0 && capacity_rows % block_x == 0, "moe_grouped_gemm: capacity_rows must be a multiple of block_x");
+  B200_REQUIRE(!silu_mul || row_scale == nullptr, "moe_grouped_gemm: silu_mul and row_scale are exclusive");
+  B200_REQUIRE(ldx >= K && ldw >= K && ldy >= (silu_mul ? N / 2 : N), "moe_grouped_gemm: leading dimensions too small");
+  B200_REQUIRE(tile_expert && num_tiles, "moe_grouped_gemm: null tile tables");
+  const DeviceInfo& d = device_info();
+  if (!d.valid || d.cc_major != 10) {
+    b200_set_error("moe_grouped_gemm: tcgen05 kernel needs an sm_100 device (found cc %d.%d)", d.cc_major, d.cc_minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define B200_GRP_CASE(BX)                                                                                     \
+  case BX:                                                                                                    \
+    return silu_mul ? launch_gemm_grouped<BX, 1>(X, W, Y, capacity_rows, N, K, num_experts, ldx, ldw, ldy,    \
+                                                 nullptr, tile_expert, num_tiles, s)                          \
+                    : launch_gemm_grouped<BX, 0>(X, W, Y, capacity_rows, N, K, num_experts, ldx, ldw, ldy,    \
+                                                 row_scale, tile_expert, num_tiles, s);
+  switch (block_x) {
+    B200_GRP_CASE(32)
+    B200_GRP_CASE(64)
+    B200_GRP_CASE(128)
+    B200_GRP_CASE(256)
+    default:
+      b200_set_error("moe_grouped_gemm: block_x=%d unsupported (32,64,128,256)", block_x);
+      return B200_ERR_INVALID;
+  }
+#undef B200_GRP_CASE
 }

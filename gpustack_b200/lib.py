@@ -40,6 +40,13 @@ SIGNATURES = {
     "b200_gemm_bf16_silu_mul": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp]),
     "b200_gemm_fp8": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200_quant_fp8_per_token": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp]),
+    "b200_moe_route": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b200_moe_capacity_rows": (_i32, [_i32, _i32, _i32]),
+    "b200_moe_align": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_moe_gather": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_moe_grouped_gemm": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
+                                     _i32, _i32, _vp]),
+    "b200_moe_combine": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_gemm_pick_block_x": (_i32, [_i32, _i32, _i32]),
     "b200_splitk_reduce": (_i32, [_vp, _i32, _vp, _i32, _i32, _i64, _vp]),
     "b200_gemm_suggest_splits": (_i32, [_i32, _i32, _i32]),

@@ -246,6 +246,78 @@ def gemm_fp8(xq, xscale, wq, wscale, out=None, out_dtype=torch.bfloat16, splits:
     return out
 
 
+# --------------------------------------------------------------------------------------- MoE
+def moe_block_x(n_pairs: int, num_experts: int) -> int:
+    """Row-tile width of the permuted MoE row space: about the mean rows per expert, so that the
+    padding (< block_x rows per expert) stays a small fraction of the grouped GEMMs."""
+    avg = n_pairs / max(1, num_experts)
+    for bx in (256, 128, 64):
+        if avg >= 0.75 * bx:
+            return bx
+    return 32
+
+
+def moe_capacity_rows(n_pairs: int, num_experts: int, block_x: int) -> int:
+    return load().b200_moe_capacity_rows(n_pairs, num_experts, block_x)
+
+
+class MoEWorkspace:
+    """Device buffers of one MoE dispatch (sized for `max_tokens` tokens, reused by every layer)."""
+
+    def __init__(self, max_tokens: int, top_k: int, num_experts: int, H: int, I: int, device):
+        self.top_k, self.E, self.H, self.I = top_k, num_experts, H, I
+        n_pairs = max_tokens * top_k
+        cap = max(moe_capacity_rows(n_pairs, num_experts, bx) for bx in (32, 64, 128, 256))
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=device)   # noqa: E731
+        self.capacity = cap
+        self.logits = torch.empty(max_tokens, num_experts, dtype=torch.bfloat16, device=device)
+        self.topk_ids, self.topk_w = i32(n_pairs), torch.empty(n_pairs, dtype=torch.float32, device=device)
+        self.pair_row, self.row_pair = i32(n_pairs), i32(cap)
+        self.row_weight = torch.empty(cap, dtype=torch.float32, device=device)
+        self.tile_expert, self.num_tiles = i32(cap // 32 + 1), torch.zeros(2, dtype=torch.int32, device=device)
+        self.xp = torch.empty(cap, H, dtype=torch.bfloat16, device=device)
+        self.act = torch.empty(cap, I, dtype=torch.bfloat16, device=device)
+        self.yp = torch.empty(cap, H, dtype=torch.bfloat16, device=device)
+
+
+def moe_route(router_logits, top_k: int, renormalize: bool = True, out_ids=None, out_w=None):
+    _req(router_logits, torch.bfloat16, "router_logits")
+    T, E = router_logits.shape
+    ids = torch.empty(T * top_k, dtype=torch.int32, device=router_logits.device) if out_ids is None else out_ids
+    w = torch.empty(T * top_k, dtype=torch.float32, device=router_logits.device) if out_w is None else out_w
+    check(load().b200_moe_route(_p(router_logits), _p(ids), _p(w), T, E, top_k, 1 if renormalize else 0, _stream()),
+          "moe_route")
+    return ids, w
+
+
+def moe_experts(x, router_logits, w13, w2, top_k: int, ws: MoEWorkspace, out, renormalize: bool = True):
+    """out[t] = sum_k weight_k * down_k(silu(gate_k x) * up_k x) over the top-k experts of token t.
+    x [T,H] bf16; router_logits [T,E] bf16; w13 [E*2I, H] (per expert: interleaved gate/up rows);
+    w2 [E*H, I].  Seven launches: route, align, gather, grouped gate_up+SiLU, grouped down (x routing
+    weight), combine -- no host synchronisation."""
+    T, H = x.shape
+    E, I = ws.E, ws.I
+    n_pairs = T * top_k
+    bx = moe_block_x(n_pairs, E)
+    cap = moe_capacity_rows(n_pairs, E, bx)
+    if cap > ws.capacity:
+        raise B200Error(f"moe_experts: {T} tokens exceed the workspace ({ws.capacity} rows)")
+    L, st = load(), _stream()
+    moe_route(router_logits, top_k, renormalize, out_ids=ws.topk_ids, out_w=ws.topk_w)
+    check(L.b200_moe_align(_p(ws.topk_ids), _p(ws.topk_w), n_pairs, E, bx, cap, _p(ws.pair_row), _p(ws.row_pair),
+                           _p(ws.row_weight), _p(ws.tile_expert), _p(ws.num_tiles), st), "moe_align")
+    check(L.b200_moe_gather(_p(x), _p(ws.row_pair), _p(ws.num_tiles), _p(ws.xp), H, top_k, cap, st), "moe_gather")
+    check(L.b200_moe_grouped_gemm(_p(ws.xp), _p(w13), _p(ws.act), cap, 2 * I, H, E, H, w13.stride(0), I, None,
+                                  _p(ws.tile_expert), _p(ws.num_tiles), bx, 1, st), "moe_grouped_gemm(gate_up)")
+    check(L.b200_moe_grouped_gemm(_p(ws.act), _p(w2), _p(ws.yp), cap, H, I, E, I, w2.stride(0), H, _p(ws.row_weight),
+                                  _p(ws.tile_expert), _p(ws.num_tiles), bx, 0, st), "moe_grouped_gemm(down)")
+    check(L.b200_moe_combine(_p(ws.yp), _p(ws.pair_row), _p(out), T, H, top_k, st), "moe_combine")
+    return out
+
+
+MOE_LAUNCHES = 6
+
+
 def splitk_reduce(partials, out=None):
     _req(partials, torch.float32, "partials")
     S, M, N = partials.shape

@@ -122,6 +122,36 @@ int b200_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, int K, in
  *   scales[t] = max(absmax(x[t,:]) / 448, 1/(448*512));  q[t,k] = e4m3(x[t,k] * (1/scales[t])), RNE, saturating. */
 int b200_quant_fp8_per_token(const void* x, int64_t ldx, void* q, int64_t ldq, float* scales, int T, int K,
                              void* stream);
+/* ---- mixture of experts (Mixtral family): MixtralMoE -> FusedMoE, $VLLM/model_executor/models/
+ * mixtral.py, $VLLM/model_executor/layers/fused_moe/ (topk_softmax, moe_align_block_size,
+ * fused_experts, moe_sum).  Everything stays on the device; tile counts are read by the grouped
+ * GEMM from device memory, so a MoE layer is CUDA-graph capturable. ---- */
+/* topk_w[t,:] = (renormalised) top-K of softmax(float(router_logits[t,:])), router_logits bf16 [T,E];
+ * topk_ids int32 [T,K]; ties go to the lowest expert index.  E <= 64, K <= 8. */
+int b200_moe_route(const void* router_logits, int32_t* topk_ids, float* topk_w, int T, int E, int K,
+                   int renormalize, void* stream);
+/* Rows the permuted space can need for n_pairs (token,k) pairs: every expert is padded to whole
+ * tiles of block_x rows. */
+int b200_moe_capacity_rows(int n_pairs, int E, int block_x);
+/* Group the pairs by expert.  pair_row [n_pairs] = row of each pair; row_pair [capacity_rows] = pair of
+ * each row (-1 = padding); row_weight [capacity_rows] = routing weight (0 = padding); tile_expert
+ * [capacity_rows / block_x] = owner of each tile; num_tiles[0] = tiles in use, [1] = rows in use. */
+int b200_moe_align(const int32_t* topk_ids, const float* topk_w, int n_pairs, int E, int block_x,
+                   int capacity_rows, int32_t* pair_row, int32_t* row_pair, float* row_weight,
+                   int32_t* tile_expert, int32_t* num_tiles, void* stream);
+/* xp[row,:] = x[row_pair[row] / K, :] (zeros for padding rows) for the rows in use. */
+int b200_moe_gather(const void* x, const int32_t* row_pair, const int32_t* num_tiles, void* xp, int H, int K,
+                    int capacity_rows, void* stream);
+/* Grouped tcgen05 GEMM over the permuted rows: Y[row,:] = X[row,:] * W[tile_expert[row / block_x]]^T.
+ * W [num_experts * N, K] bf16 (experts stacked, N % 256 == 0, K % 64 == 0).  row_scale (optional)
+ * multiplies each row's fp32 accumulator (routing weight); silu_mul != 0: W rows are interleaved
+ * gate/up and Y is [capacity_rows, N/2] (as b200_gemm_bf16_silu_mul). */
+int b200_moe_grouped_gemm(const void* X, const void* W, void* Y, int capacity_rows, int N, int K,
+                          int num_experts, int64_t ldx, int64_t ldw, int64_t ldy, const float* row_scale,
+                          const int32_t* tile_expert, const int32_t* num_tiles, int block_x, int silu_mul,
+                          void* stream);
+/* out[t,:] = bf16(sum_j float(yp[pair_row[t*K+j], :]))  (moe_sum). */
+int b200_moe_combine(const void* yp, const int32_t* pair_row, void* out, int T, int H, int K, void* stream);
 /* Y[m,n] = bf16(sum_s partials[s][m][n]). */
 int b200_splitk_reduce(const float* partials, int splits, void* Y, int M, int N, int64_t ldy,
                        void* stream);

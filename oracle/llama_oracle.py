@@ -116,6 +116,18 @@ def fp8_linear(x: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor, b: Opti
     return y.to(x.dtype)
 
 
+def moe_topk(probs: torch.Tensor, k: int):
+    """top-k of each row, ties to the lowest index (what the reference's topk_softmax kernel and
+    this repo's moe_route_kernel do; torch.topk leaves tie order unspecified)."""
+    p = probs.clone()
+    vals, idx = [], []
+    for _ in range(k):
+        v, i = p.max(dim=-1)          # max returns the first maximal index on CPU
+        vals.append(v); idx.append(i)
+        p.scatter_(1, i.unsqueeze(1), -1.0)
+    return torch.stack(vals, dim=1), torch.stack(idx, dim=1)
+
+
 def attention_ref(q, k, v, scale: float, q_pos: torch.Tensor) -> torch.Tensor:
     """Causal GQA attention over a contiguous K/V history.
     q [Tq, Hq, D], k/v [Tk, Hkv, D]; query i may see keys 0..q_pos[i].  fp32 softmax.
@@ -156,6 +168,8 @@ class LlamaConfig:
     max_position_embeddings: int = 8192
     tie_word_embeddings: bool = False
     attention_bias: bool = False      # Qwen2: bias on q/k/v projections
+    num_local_experts: int = 0        # Mixtral: experts per MoE layer (0 = dense MLP)
+    num_experts_per_tok: int = 0
 
     @property
     def q_size(self):
@@ -179,6 +193,9 @@ TINY_QWEN2 = LlamaConfig(vocab_size=1000, hidden_size=896, intermediate_size=102
                          num_attention_heads=14, num_key_value_heads=2, head_dim=64, rms_norm_eps=1e-6,
                          rope_theta=1e6, max_position_embeddings=512, tie_word_embeddings=True,
                          attention_bias=True)
+TINY_MIXTRAL = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=256, num_hidden_layers=2,
+                           num_attention_heads=8, num_key_value_heads=2, head_dim=64, rope_theta=1e6,
+                           max_position_embeddings=512, num_local_experts=8, num_experts_per_tok=2)
 LLAMA3_8B = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
                         num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, head_dim=128)
 
@@ -206,6 +223,15 @@ def init_weights(cfg: LlamaConfig, seed: int = 0, std: float = 0.02, device="cpu
             w[p + "self_attn.v_proj.bias"] = rnd(cfg.kv_size, s=0.5)
         w[p + "self_attn.o_proj.weight"] = rnd(H, cfg.q_size)
         w[p + "post_attention_layernorm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
+        if cfg.num_local_experts:
+            # classic Mixtral checkpoint naming: w1 = gate, w3 = up, w2 = down; the router weight is
+            # drawn wider so that the top-k choice is well separated for most tokens
+            w[p + "block_sparse_moe.gate.weight"] = rnd(cfg.num_local_experts, H, s=0.2)
+            for e in range(cfg.num_local_experts):
+                w[p + f"block_sparse_moe.experts.{e}.w1.weight"] = rnd(I, H)
+                w[p + f"block_sparse_moe.experts.{e}.w3.weight"] = rnd(I, H)
+                w[p + f"block_sparse_moe.experts.{e}.w2.weight"] = rnd(H, I)
+            continue
         w[p + "mlp.gate_proj.weight"] = rnd(I, H)
         w[p + "mlp.up_proj.weight"] = rnd(I, H)
         w[p + "mlp.down_proj.weight"] = rnd(H, I)
@@ -282,6 +308,9 @@ class OracleLlama:
             a = attention_ref(q, hist[l][0], hist[l][1], scale, pos).reshape(T, cfg.q_size)
             h = self._lin(a, p + "self_attn.o_proj.weight")
             x, res = fused_add_rms_norm(h, res, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
+            if cfg.num_local_experts:
+                h = self._moe(x, p + "block_sparse_moe.")
+                continue
             gu = torch.cat((self._lin(x, p + "mlp.gate_proj.weight"), self._lin(x, p + "mlp.up_proj.weight")), dim=-1)
             h = self._lin(silu_and_mul(gu), p + "mlp.down_proj.weight")
         x, _ = fused_add_rms_norm(h, res, w["model.norm.weight"], cfg.rms_norm_eps)
@@ -289,6 +318,31 @@ class OracleLlama:
             x = x[-1:]
         lm = self.wf.get("lm_head.weight")
         return x.to(torch.float32) @ (lm if lm is not None else self.lm_head.to(torch.float32)).t()
+
+    def _moe(self, x: torch.Tensor, p: str) -> torch.Tensor:
+        """MixtralMoE.forward ($VLLM/model_executor/models/mixtral.py) -> FusedMoE: the router is a
+        plain linear in the model dtype; fused_topk takes softmax in fp32, the top-k (ties -> lowest
+        index) and renormalises; fused_experts computes silu(w1 x) * w3 x and w2 (.) per expert with
+        the routing weight applied to the fp32 accumulator before the bf16 store
+        (MUL_ROUTED_WEIGHT), and moe_sum adds the k rows of a token."""
+        cfg = self.cfg
+        logits = self._lin(x, p + "gate.weight")                      # bf16 [T, E]
+        probs = torch.softmax(logits.to(torch.float32), dim=-1)
+        topw, topi = moe_topk(probs, cfg.num_experts_per_tok)
+        topw = topw / topw.sum(dim=-1, keepdim=True)
+        out = torch.zeros(x.shape[0], cfg.hidden_size, dtype=torch.float32)
+        for e in range(cfg.num_local_experts):
+            tok, slot = torch.nonzero(topi == e, as_tuple=True)
+            if tok.numel() == 0:
+                continue
+            xe = x[tok]
+            gu = torch.cat((self._lin(xe, p + f"experts.{e}.w1.weight"), self._lin(xe, p + f"experts.{e}.w3.weight")), dim=-1)
+            act = silu_and_mul(gu)
+            w2 = self.wf.get(p + f"experts.{e}.w2.weight")
+            w2 = w2 if w2 is not None else self.w[p + f"experts.{e}.w2.weight"].to(torch.float32)
+            y = (act.to(torch.float32) @ w2.t()) * topw[tok, slot].unsqueeze(-1)
+            out.index_add_(0, tok, _bf(y))                            # bf16 rows, summed in fp32
+        return out.to(x.dtype)
 
     def _lin(self, x: torch.Tensor, name: str) -> torch.Tensor:
         wf = self.wf.get(name)

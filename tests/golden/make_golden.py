@@ -137,8 +137,52 @@ def tiny_qwen2_from_hf():
     print("wrote tiny_qwen2_hf.pt")
 
 
+def tiny_mixtral_from_hf():
+    """Mixtral family (BASELINE.json configs[4]): 8 experts, top-2 routing with renormalisation.
+    transformers 5.x keeps the experts fused in memory (mlp.experts.gate_up_proj [E, 2I, H] = gate
+    rows then up rows, mlp.experts.down_proj [E, H, I], router mlp.gate.weight); checkpoints -- and
+    the oracle -- use the classic block_sparse_moe.experts.{e}.w1/w3/w2 names."""
+    from transformers import MixtralConfig, MixtralForCausalLM
+
+    cfg = O.TINY_MIXTRAL
+    weights = O.init_weights(cfg, seed=7)
+    hf_cfg = MixtralConfig(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim, rms_norm_eps=cfg.rms_norm_eps,
+        rope_theta=cfg.rope_theta, max_position_embeddings=cfg.max_position_embeddings,
+        num_local_experts=cfg.num_local_experts, num_experts_per_tok=cfg.num_experts_per_tok,
+        sliding_window=None, tie_word_embeddings=False, router_jitter_noise=0.0, attn_implementation="eager")
+    sd = {}
+    E = cfg.num_local_experts
+    for k, v in weights.items():
+        if "block_sparse_moe" not in k:
+            sd[k] = v
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        sd[p + "mlp.gate.weight"] = weights[p + "block_sparse_moe.gate.weight"]
+        sd[p + "mlp.experts.gate_up_proj"] = torch.stack([
+            torch.cat([weights[p + f"block_sparse_moe.experts.{e}.w1.weight"],
+                       weights[p + f"block_sparse_moe.experts.{e}.w3.weight"]]) for e in range(E)])
+        sd[p + "mlp.experts.down_proj"] = torch.stack([weights[p + f"block_sparse_moe.experts.{e}.w2.weight"]
+                                                       for e in range(E)])
+    g = torch.Generator().manual_seed(44)
+    prompt = torch.randint(3, cfg.vocab_size, (1, 29), generator=g)
+    res = {"prompt": prompt[0].tolist()}
+    for dt, key in ((torch.float32, "fp32"), (BF, "bf16")):
+        model = MixtralForCausalLM(hf_cfg).to(dt).eval()
+        model.load_state_dict({k: v.to(dt) for k, v in sd.items()}, strict=True)
+        with torch.no_grad():
+            res[f"logits_{key}"] = model(prompt).logits[0].float()[-4:].clone()
+            gen = model.generate(prompt, max_new_tokens=10, do_sample=False, pad_token_id=0)
+        res[f"greedy_{key}"] = gen[0, prompt.shape[1]:].tolist()
+    torch.save(res, OUT / "tiny_mixtral_hf.pt")
+    print("wrote tiny_mixtral_hf.pt")
+
+
 if __name__ == "__main__":
     ops_from_vllm()
     fp8_quant_from_vllm()
     tiny_llama_from_hf()
     tiny_qwen2_from_hf()
+    tiny_mixtral_from_hf()
