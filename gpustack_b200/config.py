@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Optional
 
-SUPPORTED_ARCHS = ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM")
+SUPPORTED_ARCHS = ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM", "MixtralForCausalLM")
 
 
 @dataclass
@@ -34,6 +34,9 @@ class ModelConfig:
     eos_token_id: Optional[int] = None
     bos_token_id: Optional[int] = None
     quantization: Optional[str] = None       # "fp8" when config.json carries an fp8 quantization_config
+    num_local_experts: int = 0               # Mixtral: experts per layer (0 = dense MLP)
+    sliding_window: Optional[int] = None     # caps max_model_len (full attention == windowed below it)
+    num_experts_per_tok: int = 0
 
     @property
     def q_size(self) -> int:
@@ -49,7 +52,8 @@ class ModelConfig:
     def weight_bytes(self, tp: int = 1) -> int:
         """bf16 bytes streamed per decode step on one rank (layers + lm_head + final norm)."""
         H, I = self.hidden_size, self.intermediate_size
-        per_layer = (self.q_size + 2 * self.kv_size) * H + self.q_size * H + 3 * I * H
+        mlp = 3 * I * H * max(1, self.num_local_experts) + self.num_local_experts * H * tp   # all experts hot
+        per_layer = (self.q_size + 2 * self.kv_size) * H + self.q_size * H + mlp
         norms = (2 * self.num_hidden_layers + 1) * H          # replicated
         return 2 * (self.num_hidden_layers * per_layer // tp + self.vocab_size * H // tp + norms)
 
@@ -79,8 +83,15 @@ class ModelConfig:
                 raise ValueError(f"unsupported quantization_config {qc}: only quant_method=fp8, "
                                  "activation_scheme=dynamic, per-tensor weights are supported")
             quant = "fp8"
+        n_exp = int(d.get("num_local_experts") or 0) if arch == "MixtralForCausalLM" else 0
+        if n_exp and quant:
+            raise ValueError("fp8 quantisation of mixture-of-experts models is not supported yet")
+        # sliding-window attention is not implemented: a model that uses it is served with the
+        # context capped at the window, where full attention is the same computation
+        window = d.get("sliding_window") if d.get("use_sliding_window", True) else None
         return ModelConfig(
-            quantization=quant,
+            quantization=quant, num_local_experts=n_exp, sliding_window=int(window) if window else None,
+            num_experts_per_tok=int(d.get("num_experts_per_tok") or 0) if n_exp else 0,
             vocab_size=d["vocab_size"], hidden_size=d["hidden_size"],
             intermediate_size=d["intermediate_size"], num_hidden_layers=d["num_hidden_layers"],
             num_attention_heads=heads, num_key_value_heads=d.get("num_key_value_heads", heads),
@@ -99,9 +110,14 @@ class ModelConfig:
     def to_hf_dict(self) -> dict:
         extra = {"quantization_config": {"quant_method": "fp8", "activation_scheme": "dynamic"}} \
             if self.quantization == "fp8" else {}
+        if self.num_local_experts:
+            extra.update({"num_local_experts": self.num_local_experts, "num_experts_per_tok": self.num_experts_per_tok,
+                          "sliding_window": None})
+        model_type = {"MixtralForCausalLM": "mixtral", "Qwen2ForCausalLM": "qwen2", "MistralForCausalLM": "mistral"} \
+            .get(self.architecture, "llama")
         return {
             **extra,
-            "architectures": [self.architecture], "model_type": "llama", "vocab_size": self.vocab_size,
+            "architectures": [self.architecture], "model_type": model_type, "vocab_size": self.vocab_size,
             "hidden_size": self.hidden_size, "intermediate_size": self.intermediate_size,
             "num_hidden_layers": self.num_hidden_layers, "num_attention_heads": self.num_attention_heads,
             "num_key_value_heads": self.num_key_value_heads, "head_dim": self.head_dim,
@@ -119,6 +135,20 @@ def llama3_8b() -> ModelConfig:
                        num_attention_heads=32, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
                        rope_theta=500000.0, max_position_embeddings=8192, eos_token_id=128001,
                        bos_token_id=128000)
+
+
+def tiny_mixtral() -> ModelConfig:
+    return ModelConfig(vocab_size=512, hidden_size=512, intermediate_size=256, num_hidden_layers=2,
+                       num_attention_heads=8, num_key_value_heads=2, head_dim=64, rope_theta=1e6,
+                       max_position_embeddings=512, eos_token_id=2, bos_token_id=1,
+                       architecture="MixtralForCausalLM", num_local_experts=8, num_experts_per_tok=2)
+
+
+def mixtral_8x7b() -> ModelConfig:
+    return ModelConfig(vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                       num_attention_heads=32, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
+                       rope_theta=1e6, max_position_embeddings=32768, eos_token_id=2, bos_token_id=1,
+                       architecture="MixtralForCausalLM", num_local_experts=8, num_experts_per_tok=2)
 
 
 def tiny_llama(head_dim: int = 64) -> ModelConfig:

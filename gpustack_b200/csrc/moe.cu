@@ -21,8 +21,8 @@ constexpr int kMaxTopK = 8;
 // ---------------------------------------------------------------------------------------------
 // topk_w[t, :] = renormalised top-k of softmax(float(logits[t, :])); ties -> lowest expert index.
 __global__ void __launch_bounds__(128)
-moe_route_kernel(const bf16* __restrict__ logits, int32_t* __restrict__ topk_ids, float* __restrict__ topk_w,
-                 int T, int E, int K, int renormalize) {
+moe_route_kernel(const bf16* __restrict__ logits, int64_t ld, int32_t* __restrict__ topk_ids,
+                 float* __restrict__ topk_w, int T, int E, int K, int renormalize) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,7 +30,7 @@ moe_route_kernel(const bf16* __restrict__ logits, int32_t* __restrict__ topk_ids
   float p[kMaxExperts];
   float mx = -INFINITY;
   for (int e = 0; e < E; ++e) {
-    p[e] = __bfloat162float(logits[(size_t)t * E + e]);
+    p[e] = __bfloat162float(logits[(size_t)t * ld + e]);
     mx = fmaxf(mx, p[e]);
   }
   float sum = 0.f;
@@ -175,13 +175,14 @@ static int moe_grid(size_t work_items, int threads) {
 
 using namespace b200;
 
-extern "C" int b200_moe_route(const void* router_logits, int32_t* topk_ids, float* topk_w, int T, int E, int K,
-                              int renormalize, void* stream) {
+extern "C" int b200_moe_route(const void* router_logits, int64_t ld, int32_t* topk_ids, float* topk_w, int T,
+                              int E, int K, int renormalize, void* stream) {
+  B200_REQUIRE(ld >= E, "moe_route: row stride %lld < E=%d", (long long)ld, E);
   B200_REQUIRE(T >= 0 && E >= 1 && E <= kMaxExperts && K >= 1 && K <= kMaxTopK && K <= E,
                "moe_route: unsupported E=%d K=%d (E <= %d, K <= %d)", E, K, kMaxExperts, kMaxTopK);
   if (T == 0) return B200_OK;
   (void)launch_pdl(moe_route_kernel, dim3((T + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1,
-                   (const bf16*)router_logits, topk_ids, topk_w, T, E, K, renormalize);
+                   (const bf16*)router_logits, ld, topk_ids, topk_w, T, E, K, renormalize);
   return b200_check_launch("b200_moe_route");
 }
 

@@ -8,6 +8,7 @@ kernel sequence on their weight / KV shards (TPWorker.serve_forever).
 """
 from __future__ import annotations
 
+import logging
 import os
 import time
 from typing import Dict, Iterable, List, Optional, Sequence
@@ -20,6 +21,8 @@ from .lib import B200Error
 from .runner import ModelRunner
 from .scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
 from .weights import ModelWeights, load_safetensors_dir, random_state_dict, shard_state_dict
+
+log = logging.getLogger("b200.engine")
 
 _KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED = 0, 1, 2, 3, 4
 
@@ -169,6 +172,10 @@ class LLMEngine:
         if ecfg.max_model_len is None:
             ecfg.max_model_len = mcfg.max_position_embeddings
         ecfg.max_model_len = min(ecfg.max_model_len, mcfg.max_position_embeddings)
+        if mcfg.sliding_window and ecfg.max_model_len > mcfg.sliding_window:
+            log.warning("sliding-window attention is not implemented: max_model_len capped at the window (%d)",
+                        mcfg.sliding_window)
+            ecfg.max_model_len = mcfg.sliding_window
         self.runner = ModelRunner(mcfg, ecfg, weights, device=device, tp_group=tp.nccl if tp else None, tp_ctx=tp)
         n = self.runner.profile_num_blocks()
         if tp:   # every rank must use the same block count

@@ -40,7 +40,7 @@ SIGNATURES = {
     "b200_gemm_bf16_silu_mul": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp]),
     "b200_gemm_fp8": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200_quant_fp8_per_token": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp]),
-    "b200_moe_route": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b200_moe_route": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200_moe_capacity_rows": (_i32, [_i32, _i32, _i32]),
     "b200_moe_align": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_moe_gather": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -247,6 +247,16 @@ def gemm_fp8(xq, xscale, wq, wscale, out=None, out_dtype=torch.bfloat16, splits:
 
 
 # --------------------------------------------------------------------------------------- MoE
+ROUTER_PAD = 128   # the router weight is zero-padded to one full weight tile of the GEMM
+
+
+def pad_router(router: torch.Tensor) -> torch.Tensor:
+    """[E, H] -> [128, H] with zero rows, so the router projection is an ordinary one-tile GEMM."""
+    out = torch.zeros(ROUTER_PAD, router.shape[1], dtype=router.dtype, device=router.device)
+    out[: router.shape[0]] = router
+    return out
+
+
 def moe_block_x(n_pairs: int, num_experts: int) -> int:
     """Row-tile width of the permuted MoE row space: about the mean rows per expert, so that the
     padding (< block_x rows per expert) stays a small fraction of the grouped GEMMs."""
@@ -270,7 +280,7 @@ class MoEWorkspace:
         cap = max(moe_capacity_rows(n_pairs, num_experts, bx) for bx in (32, 64, 128, 256))
         i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=device)   # noqa: E731
         self.capacity = cap
-        self.logits = torch.empty(max_tokens, num_experts, dtype=torch.bfloat16, device=device)
+        self.logits = torch.empty(max_tokens, ROUTER_PAD, dtype=torch.bfloat16, device=device)
         self.topk_ids, self.topk_w = i32(n_pairs), torch.empty(n_pairs, dtype=torch.float32, device=device)
         self.pair_row, self.row_pair = i32(n_pairs), i32(cap)
         self.row_weight = torch.empty(cap, dtype=torch.float32, device=device)
@@ -280,19 +290,23 @@ class MoEWorkspace:
         self.yp = torch.empty(cap, H, dtype=torch.bfloat16, device=device)
 
 
-def moe_route(router_logits, top_k: int, renormalize: bool = True, out_ids=None, out_w=None):
-    _req(router_logits, torch.bfloat16, "router_logits")
-    T, E = router_logits.shape
+def moe_route(router_logits, top_k: int, renormalize: bool = True, out_ids=None, out_w=None,
+              num_experts: Optional[int] = None):
+    """router_logits [T, >=E] bf16 (columns beyond num_experts are padding of the router GEMM)."""
+    if not router_logits.is_cuda or router_logits.dtype != torch.bfloat16 or router_logits.stride(1) != 1:
+        raise B200Error("moe_route: bf16 CUDA logits with contiguous rows required")
+    T = router_logits.shape[0]
+    E = router_logits.shape[1] if num_experts is None else num_experts
     ids = torch.empty(T * top_k, dtype=torch.int32, device=router_logits.device) if out_ids is None else out_ids
     w = torch.empty(T * top_k, dtype=torch.float32, device=router_logits.device) if out_w is None else out_w
-    check(load().b200_moe_route(_p(router_logits), _p(ids), _p(w), T, E, top_k, 1 if renormalize else 0, _stream()),
-          "moe_route")
+    check(load().b200_moe_route(_p(router_logits), router_logits.stride(0), _p(ids), _p(w), T, E, top_k,
+                                1 if renormalize else 0, _stream()), "moe_route")
     return ids, w
 
 
 def moe_experts(x, router_logits, w13, w2, top_k: int, ws: MoEWorkspace, out, renormalize: bool = True):
     """out[t] = sum_k weight_k * down_k(silu(gate_k x) * up_k x) over the top-k experts of token t.
-    x [T,H] bf16; router_logits [T,E] bf16; w13 [E*2I, H] (per expert: interleaved gate/up rows);
+    x [T,H] bf16; router_logits [T,>=E] bf16; w13 [E*2I, H] (per expert: interleaved gate/up rows);
     w2 [E*H, I].  Seven launches: route, align, gather, grouped gate_up+SiLU, grouped down (x routing
     weight), combine -- no host synchronisation."""
     T, H = x.shape
@@ -303,7 +317,7 @@ def moe_experts(x, router_logits, w13, w2, top_k: int, ws: MoEWorkspace, out, re
     if cap > ws.capacity:
         raise B200Error(f"moe_experts: {T} tokens exceed the workspace ({ws.capacity} rows)")
     L, st = load(), _stream()
-    moe_route(router_logits, top_k, renormalize, out_ids=ws.topk_ids, out_w=ws.topk_w)
+    moe_route(router_logits, top_k, renormalize, out_ids=ws.topk_ids, out_w=ws.topk_w, num_experts=E)
     check(L.b200_moe_align(_p(ws.topk_ids), _p(ws.topk_w), n_pairs, E, bx, cap, _p(ws.pair_row), _p(ws.row_pair),
                            _p(ws.row_weight), _p(ws.tile_expert), _p(ws.num_tiles), st), "moe_align")
     check(L.b200_moe_gather(_p(x), _p(ws.row_pair), _p(ws.num_tiles), _p(ws.xp), H, top_k, cap, st), "moe_gather")

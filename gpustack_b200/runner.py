@@ -87,6 +87,9 @@ class ModelRunner:
         self.qkv = e(T, self.qkv_width)
         self.attn_out = e(T, self.Hq * self.D)
         self.act = e(T, self.I)
+        self.moe_ws = None
+        if self.mcfg.num_local_experts:
+            self.moe_ws = ops.MoEWorkspace(T, self.mcfg.num_experts_per_tok, self.mcfg.num_local_experts, H, self.I, dev)
         if self.fp8:
             kmax = max(H, self.Hq * self.D, self.I)
             self.xq = e(T * kmax, dt=ops.FP8)          # flat; viewed [T, K] per projection
@@ -220,10 +223,30 @@ class ModelRunner:
                                   self.Hq, self.Hkv, self.D)
             attn_fn(l)
             self._row_parallel(self.attn_out[:T], lw.o, T, lw.post_norm)
-            ops.gemm_silu_mul(self.xn[:T], lw.gate_up, out=self.act[:T])   # SiLU*mul in the epilogue
             nxt = w.layers[l + 1].input_norm if l + 1 < len(w.layers) else w.final_norm
+            if lw.router is not None:
+                self._moe(T, lw, nxt)
+                self.stats["kernel_launches"] += 2
+                continue
+            ops.gemm_silu_mul(self.xn[:T], lw.gate_up, out=self.act[:T])   # SiLU*mul in the epilogue
             self._row_parallel(self.act[:T], lw.down, T, nxt)
             self.stats["kernel_launches"] += 4
+
+    def _moe(self, T: int, lw, norm_w: torch.Tensor) -> None:
+        """Mixtral sparse MLP (MixtralMoE.forward, $VLLM/model_executor/models/mixtral.py): router
+        linear -> top-k softmax routing -> grouped expert GEMMs over the permuted rows -> combine,
+        then (all-reduce +) residual add + RMSNorm -> self.xn.  Experts are tensor-parallel over I
+        like the dense MLP, so the combine output is this rank's partial sum."""
+        eps = self.mcfg.rms_norm_eps
+        ws = self.moe_ws
+        ops.gemm(self.xn[:T], lw.router, out=ws.logits[:T])
+        ops.moe_experts(self.xn[:T], ws.logits[:T], lw.w13, lw.w2, self.mcfg.num_experts_per_tok, ws, out=self.hbuf[:T])
+        self.stats["kernel_launches"] += 1 + ops.MOE_LAUNCHES
+        if self.tp > 1:
+            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
+            self.stats["kernel_launches"] += 1
+        ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T], residual_out=self.resid[:T])
+        self.stats["kernel_launches"] += 1
 
     def _layer_fp8(self, T: int, l: int, lw, attn_fn) -> None:
         """One decoder layer with W8A8 linears (Fp8LinearMethod.apply,

@@ -38,13 +38,18 @@ class LayerWeights:
     qkv_bias: Optional[torch.Tensor]
     o: torch.Tensor               # [H, Hq/t * D]
     post_norm: torch.Tensor       # [H]
-    gate_up: torch.Tensor         # [2I/t, H]  rows interleaved: 2i = gate_i, 2i+1 = up_i (fused SiLU*mul epilogue)
-    down: torch.Tensor            # [H, I/t]
+    gate_up: Optional[torch.Tensor]   # [2I/t, H]  rows interleaved: 2i = gate_i, 2i+1 = up_i (fused SiLU*mul epilogue)
+    down: Optional[torch.Tensor]      # [H, I/t]
     # fp8 mode: the four matrices above are float8_e4m3fn and these hold their fp32 scales ([1])
     qkv_scale: Optional[torch.Tensor] = None
     o_scale: Optional[torch.Tensor] = None
     gate_up_scale: Optional[torch.Tensor] = None
     down_scale: Optional[torch.Tensor] = None
+    # Mixtral (gate_up / down are None): router replicated, experts stacked along the rows and
+    # tensor-parallel over I exactly like the dense MLP
+    router: Optional[torch.Tensor] = None      # [128, H]: E router rows, zero-padded to a GEMM tile
+    w13: Optional[torch.Tensor] = None         # [E * 2I/t, H]  per expert: interleaved gate (w1) / up (w3) rows
+    w2: Optional[torch.Tensor] = None          # [E * H, I/t]
 
 
 @dataclass
@@ -141,14 +146,41 @@ def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank:
                                   ksl(get(p + "self_attn.v_proj.bias"))]))
         qkv_w, qkv_s = fuse([p + f"self_attn.{n}_proj.weight" for n in "qkv"], [qsl, ksl, ksl])
         o_w, o_s = fuse([p + "self_attn.o_proj.weight"], [lambda t: t[:, rank * hq * D:(rank + 1) * hq * D]])
-        gu_w, gu_s = fuse([p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight"], [isl, isl], interleave=True)
-        down_w, down_s = fuse([p + "mlp.down_proj.weight"], [lambda t: t[:, rank * I:(rank + 1) * I]])
+        moe = {}
+        gu_w = gu_s = down_w = down_s = None
+        if cfg.num_local_experts:
+            if fp8:
+                raise ValueError("fp8 quantisation of mixture-of-experts models is not supported yet")
+            E = cfg.num_local_experts
+            m = p + "block_sparse_moe."
+            if has is not None and not has(m + "gate.weight") and has(p + "mlp.experts.gate_up_proj"):
+                # transformers >= 5 export: experts fused as [E, 2I, H] (gate rows, then up rows) / [E, H, I]
+                gup, dn = get(p + "mlp.experts.gate_up_proj"), get(p + "mlp.experts.down_proj")
+                Ifull = cfg.intermediate_size
+                w1 = [gup[e, :Ifull] for e in range(E)]
+                w3 = [gup[e, Ifull:] for e in range(E)]
+                w2 = [dn[e] for e in range(E)]
+                router = get(p + "mlp.gate.weight")
+            else:
+                w1 = [get(m + f"experts.{e}.w1.weight") for e in range(E)]
+                w3 = [get(m + f"experts.{e}.w3.weight") for e in range(E)]
+                w2 = [get(m + f"experts.{e}.w2.weight") for e in range(E)]
+                router = get(m + "gate.weight")
+            w13 = torch.cat([torch.stack([isl(w1[e]).to(device), isl(w3[e]).to(device)], dim=1).reshape(2 * I, -1)
+                             for e in range(E)], dim=0)
+            router_pad = torch.zeros(128, router.shape[1], dtype=BF16)     # one full GEMM weight tile
+            router_pad[:E] = router.to(BF16)
+            moe = dict(router=dev(router_pad), w13=dev(w13),
+                       w2=dev(torch.cat([w2[e][:, rank * I:(rank + 1) * I].to(device) for e in range(E)], dim=0)))
+        else:
+            gu_w, gu_s = fuse([p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight"], [isl, isl], interleave=True)
+            down_w, down_s = fuse([p + "mlp.down_proj.weight"], [lambda t: t[:, rank * I:(rank + 1) * I]])
         layers.append(LayerWeights(
             input_norm=dev(get(p + "input_layernorm.weight")),
             qkv=qkv_w, qkv_bias=bias, o=o_w,
             post_norm=dev(get(p + "post_attention_layernorm.weight")),
             gate_up=gu_w, down=down_w,
-            qkv_scale=qkv_s, o_scale=o_s, gate_up_scale=gu_s, down_scale=down_s))
+            qkv_scale=qkv_s, o_scale=o_s, gate_up_scale=gu_s, down_scale=down_s, **moe))
     embed = dev(get("model.embed_tokens.weight"))
     V = cfg.vocab_size
     per = (V + tp - 1) // tp
@@ -209,6 +241,13 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, std: float = 0.02, device
                 w[p + f"self_attn.{n}_proj.bias"] = rnd(sz)
         w[p + "self_attn.o_proj.weight"] = rnd(H, cfg.q_size)
         w[p + "post_attention_layernorm.weight"] = (1.0 + rnd(H, s=0.1).float()).to(BF16)
+        if cfg.num_local_experts:
+            w[p + "block_sparse_moe.gate.weight"] = rnd(cfg.num_local_experts, H, s=0.2)
+            for e in range(cfg.num_local_experts):
+                w[p + f"block_sparse_moe.experts.{e}.w1.weight"] = rnd(I, H)
+                w[p + f"block_sparse_moe.experts.{e}.w3.weight"] = rnd(I, H)
+                w[p + f"block_sparse_moe.experts.{e}.w2.weight"] = rnd(H, I)
+            continue
         w[p + "mlp.gate_proj.weight"] = rnd(I, H)
         w[p + "mlp.up_proj.weight"] = rnd(I, H)
         w[p + "mlp.down_proj.weight"] = rnd(H, I)

@@ -126,10 +126,10 @@ int b200_quant_fp8_per_token(const void* x, int64_t ldx, void* q, int64_t ldq, f
  * mixtral.py, $VLLM/model_executor/layers/fused_moe/ (topk_softmax, moe_align_block_size,
  * fused_experts, moe_sum).  Everything stays on the device; tile counts are read by the grouped
  * GEMM from device memory, so a MoE layer is CUDA-graph capturable. ---- */
-/* topk_w[t,:] = (renormalised) top-K of softmax(float(router_logits[t,:])), router_logits bf16 [T,E];
- * topk_ids int32 [T,K]; ties go to the lowest expert index.  E <= 64, K <= 8. */
-int b200_moe_route(const void* router_logits, int32_t* topk_ids, float* topk_w, int T, int E, int K,
-                   int renormalize, void* stream);
+/* topk_w[t,:] = (renormalised) top-K of softmax(float(router_logits[t,:E])), router_logits bf16 with row
+ * stride ld >= E; topk_ids int32 [T,K]; ties go to the lowest expert index.  E <= 64, K <= 8. */
+int b200_moe_route(const void* router_logits, int64_t ld, int32_t* topk_ids, float* topk_w, int T, int E,
+                   int K, int renormalize, void* stream);
 /* Rows the permuted space can need for n_pairs (token,k) pairs: every expert is padded to whole
  * tiles of block_x rows. */
 int b200_moe_capacity_rows(int n_pairs, int E, int block_x);

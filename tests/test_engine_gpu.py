@@ -21,15 +21,19 @@ def _engine(cfg_o, seed=7, **kw):
                        head_dim=cfg_o.head_dim, rms_norm_eps=cfg_o.rms_norm_eps, rope_theta=cfg_o.rope_theta,
                        max_position_embeddings=cfg_o.max_position_embeddings, eos_token_id=2,
                        tie_word_embeddings=cfg_o.tie_word_embeddings, attention_bias=cfg_o.attention_bias,
-                       architecture="Qwen2ForCausalLM" if cfg_o.attention_bias else "LlamaForCausalLM")
+                       num_local_experts=cfg_o.num_local_experts, num_experts_per_tok=cfg_o.num_experts_per_tok,
+                       architecture="MixtralForCausalLM" if cfg_o.num_local_experts else
+                       "Qwen2ForCausalLM" if cfg_o.attention_bias else "LlamaForCausalLM")
     weights = O.init_weights(cfg_o, seed=seed)
     ecfg = EngineConfig(max_num_seqs=kw.pop("max_num_seqs", 16), max_num_batched_tokens=kw.pop("mbt", 256),
                         num_gpu_blocks=kw.pop("blocks", 128), **kw)
-    eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
+    sd = {k: v.cuda() for k, v in weights.items()}
+    eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict=sd)
     return eng, O.OracleLlama(cfg_o, weights, quantization=ecfg.quantization)
 
 
-@pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128, O.TINY_QWEN2], ids=["tiny64", "tiny128", "qwen2-bias-tied-g7"])
+@pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128, O.TINY_QWEN2, O.TINY_MIXTRAL],
+                         ids=["tiny64", "tiny128", "qwen2-bias-tied-g7", "mixtral-8x-top2"])
 @pytest.mark.parametrize("eager", [True, False], ids=["eager", "graphs"])
 def test_prefill_logits_and_greedy_decode(cfg_o, eager):
     from gpustack_b200.scheduler import SamplingParams

@@ -318,6 +318,81 @@ def test_gemm_fp8_vs_cpu_oracle(ops, out_dir):
     _close(y, O.fp8_linear(x, wq, ws), 1e-2, 1.6e-2, "gemm_fp8 vs oracle.fp8_linear", out_dir)
 
 
+# ------------------------------------------------------------------------------------- MoE
+@pytest.mark.parametrize("T,E,K", [(1, 8, 2), (7, 8, 2), (64, 8, 2), (300, 8, 2), (33, 4, 1), (129, 16, 4)])
+def test_moe_route_and_align(ops, T, E, K):
+    """routing == oracle (softmax in fp32, top-k with ties to the lowest index, renormalised), and the
+    permuted row space is a valid grouping: every pair owns one row inside a tile of its expert."""
+    from gpustack_b200.lib import load
+
+    g = torch.Generator().manual_seed(T + E)
+    logits = (torch.randn(T, 128, generator=g) * 2).to(BF)          # padded router output, E live columns
+    logits[0, :E] = 0.5                                              # an all-tie row
+    ids, w = ops.moe_route(logits.cuda(), K, num_experts=E)
+    rw, ri = O.moe_topk(torch.softmax(logits[:, :E].float(), dim=-1), K)
+    rw = rw / rw.sum(dim=-1, keepdim=True)
+    assert torch.equal(ids.cpu().view(T, K), ri.to(torch.int32))
+    assert float((w.cpu().view(T, K) - rw).abs().max()) <= 1e-6
+    for bx in (32, 128):
+        n_pairs = T * K
+        cap = ops.moe_capacity_rows(n_pairs, E, bx)
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device="cuda")          # noqa: E731
+        pair_row, row_pair, tile_expert, num_tiles = i32(n_pairs), i32(cap), i32(cap // bx), torch.zeros(2, dtype=torch.int32, device="cuda")
+        row_w = torch.empty(cap, dtype=torch.float32, device="cuda")
+        rc = load().b200_moe_align(ids.data_ptr(), w.data_ptr(), n_pairs, E, bx, cap, pair_row.data_ptr(), row_pair.data_ptr(),
+                                   row_w.data_ptr(), tile_expert.data_ptr(), num_tiles.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        pr, rp, te, nt, rwt = pair_row.cpu(), row_pair.cpu(), tile_expert.cpu(), num_tiles.cpu().tolist(), row_w.cpu()
+        counts = torch.bincount(ids.cpu().long(), minlength=E)
+        assert nt[0] == int(((counts + bx - 1) // bx).sum()) and nt[1] == nt[0] * bx <= cap
+        assert len(set(pr.tolist())) == n_pairs and int(pr.max()) < nt[1]
+        for i in range(n_pairs):
+            r = int(pr[i])
+            assert int(rp[r]) == i and int(te[r // bx]) == int(ids[i]) and float(rwt[r]) == float(w[i])
+        assert int((rp[: nt[1]] >= 0).sum()) == n_pairs and bool((rwt[rp < 0] == 0).all())
+        assert te[: nt[0]].tolist() == sorted(te[: nt[0]].tolist())
+
+
+@pytest.mark.parametrize("T,E,K,H,I", [(1, 8, 2, 512, 256), (7, 8, 2, 512, 256), (64, 8, 2, 512, 256),
+                                         (300, 8, 2, 512, 256), (40, 4, 1, 1024, 512), (257, 8, 2, 4096, 1792),
+                                         (2100, 8, 2, 1024, 512)])
+def test_moe_experts_vs_oracle(ops, T, E, K, H, I, out_dir):
+    """route -> align -> gather -> grouped gate_up+SiLU -> grouped down (x routing weight) -> combine
+    against the oracle's per-expert loop (same roundings: bf16 gate/up, bf16 act, fp32 acc x weight
+    -> bf16 row, fp32 sum of the k rows -> bf16)."""
+    g = torch.Generator().manual_seed(T * 3 + E + H)
+    x = torch.randn(T, H, generator=g).to(BF)
+    router = (torch.randn(E, H, generator=g) * 0.2).to(BF)
+    w1 = [(torch.randn(I, H, generator=g) * 0.03).to(BF) for _ in range(E)]
+    w3 = [(torch.randn(I, H, generator=g) * 0.03).to(BF) for _ in range(E)]
+    w2 = [(torch.randn(H, I, generator=g) * 0.03).to(BF) for _ in range(E)]
+    ws = ops.MoEWorkspace(T, K, E, H, I, "cuda")
+    xc = x.cuda()
+    logits = ops.gemm(xc, ops.pad_router(router.cuda()), out=ws.logits[:T])
+    assert torch.equal(logits[:, :E].cpu(), O.linear(x, router)) or \
+        float((logits[:, :E].cpu().float() - O.linear(x, router).float()).abs().max()) < 0.05
+    w13 = torch.cat([ops.interleave_gate_up(w1[e], w3[e]) for e in range(E)]).cuda()
+    w2s = torch.cat(w2).cuda()
+    out = torch.empty(T, H, dtype=BF, device="cuda")
+    ops.moe_experts(xc, logits, w13, w2s, K, ws, out)
+    # oracle on the GPU's own router logits (a near-tie between experts is a legitimate flip otherwise)
+    lg = logits[:, :E].cpu()
+    topw, topi = O.moe_topk(torch.softmax(lg.float(), dim=-1), K)
+    topw = topw / topw.sum(dim=-1, keepdim=True)
+    ref = torch.zeros(T, H)
+    for e in range(E):
+        tok, slot = torch.nonzero(topi == e, as_tuple=True)
+        if tok.numel() == 0:
+            continue
+        act = O.silu_and_mul(torch.cat((O.linear(x[tok], w1[e]), O.linear(x[tok], w3[e])), dim=-1))
+        y = (act.float() @ w2[e].float().t()) * topw[tok, slot].unsqueeze(-1)
+        ref.index_add_(0, tok, y.to(BF).float())
+    _close(out, ref.to(BF), 2e-2 * float(ref.abs().max()), 3.2e-2, f"moe_experts T={T} E={E} K={K}", out_dir)
+    nt = ws.num_tiles.cpu().tolist()
+    assert nt[1] >= T * K
+
+
 def test_gemm_vs_cpu_oracle(ops, out_dir):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(40, 512, generator=g).to(BF); w = (torch.randn(640, 512, generator=g) * 0.05).to(BF)

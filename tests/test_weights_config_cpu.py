@@ -97,7 +97,7 @@ def test_config_parsing_and_byte_accounting():
     m = ModelConfig.from_dict(hf)
     assert m.head_dim == 16 and m.num_key_value_heads == 4 and m.eos_token_id == 7
     with pytest.raises(ValueError):
-        ModelConfig.from_dict({**hf, "architectures": ["MixtralForCausalLM"]})
+        ModelConfig.from_dict({**hf, "architectures": ["DeepseekV3ForCausalLM"]})
     with pytest.raises(ValueError):
         ModelConfig.from_dict({**hf, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
     e = EngineConfig(max_num_seqs=100)
@@ -202,3 +202,76 @@ def test_unsupported_quantisation_configs_are_refused():
             q8[k[:-6] + "input_scale"] = torch.ones(1)
     with pytest.raises(ValueError, match="static activation"):
         shard_state_dict(cfg, lambda k: q8[k], 0, 1, "cpu", quantization="fp8", has=lambda k: k in q8)
+
+
+# ------------------------------------------------------------------------------------ Mixtral
+def test_mixtral_expert_weights_are_stacked_interleaved_and_tp_sharded():
+    from gpustack_b200.config import tiny_mixtral
+
+    cfg = tiny_mixtral()
+    sd = random_state_dict(cfg, seed=8, device="cpu")
+    E, I, H = cfg.num_local_experts, cfg.intermediate_size, cfg.hidden_size
+    full = shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu", has=lambda k: k in sd)
+    lw = full.layers[1]
+    p = "model.layers.1.block_sparse_moe."
+    assert lw.gate_up is None and lw.down is None
+    assert lw.router.shape == (128, H) and torch.equal(lw.router[:E], sd[p + "gate.weight"]) and not lw.router[E:].any()
+    assert lw.w13.shape == (E * 2 * I, H) and lw.w2.shape == (E * H, I)
+    for e in (0, 5):
+        blk = lw.w13[e * 2 * I:(e + 1) * 2 * I]
+        assert torch.equal(blk[0::2], sd[p + f"experts.{e}.w1.weight"]) and torch.equal(blk[1::2], sd[p + f"experts.{e}.w3.weight"])
+        assert torch.equal(lw.w2[e * H:(e + 1) * H], sd[p + f"experts.{e}.w2.weight"])
+    # tensor parallel over I: the two ranks' partial expert outputs sum to the full one
+    tp = 2
+    shards = [shard_state_dict(cfg, lambda k: sd[k], r, tp, "cpu", has=lambda k: k in sd) for r in range(tp)]
+    x = torch.randn(3, H)
+    e = 3
+    ref_g = x @ sd[p + f"experts.{e}.w1.weight"].float().t()
+    ref_u = x @ sd[p + f"experts.{e}.w3.weight"].float().t()
+    ref = (torch.nn.functional.silu(ref_g) * ref_u) @ sd[p + f"experts.{e}.w2.weight"].float().t()
+    acc = 0
+    for sh in shards:
+        l2 = sh.layers[1]
+        Il = I // tp
+        blk = l2.w13[e * 2 * Il:(e + 1) * 2 * Il].float()
+        gu = x @ blk.t()
+        acc = acc + (torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2]) @ l2.w2[e * H:(e + 1) * H].float().t()
+    torch.testing.assert_close(acc, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_mixtral_config_and_transformers5_fused_checkpoint_layout(tmp_path):
+    from gpustack_b200.config import mixtral_8x7b, tiny_mixtral
+
+    cfg = tiny_mixtral()
+    d = cfg.to_hf_dict()
+    assert d["model_type"] == "mixtral" and d["num_local_experts"] == 8 and d["num_experts_per_tok"] == 2
+    back = ModelConfig.from_dict(d)
+    assert back.num_local_experts == 8 and back.num_experts_per_tok == 2 and back.architecture == "MixtralForCausalLM"
+    big = mixtral_8x7b()
+    # 46,702,792,704 parameters
+    n = big.vocab_size * big.hidden_size * 2 + big.num_hidden_layers * (
+        (big.q_size + 2 * big.kv_size) * big.hidden_size + big.q_size * big.hidden_size + 8 * 3 * big.intermediate_size * big.hidden_size
+        + 8 * big.hidden_size + 2 * big.hidden_size) + big.hidden_size
+    assert n == 46_702_792_704
+    # sliding window: served with the context capped at the window
+    assert ModelConfig.from_dict({**d, "sliding_window": 256}).sliding_window == 256
+    assert ModelConfig.from_dict({**d, "sliding_window": 256, "use_sliding_window": False}).sliding_window is None
+    with pytest.raises(ValueError):
+        ModelConfig.from_dict({**d, "quantization_config": {"quant_method": "fp8"}})
+    # classic checkpoint names and the transformers-5 fused export load to the same tensors
+    sd = random_state_dict(cfg, seed=9, device="cpu")
+    fused = {k: v for k, v in sd.items() if "block_sparse_moe" not in k}
+    E = cfg.num_local_experts
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        fused[p + "mlp.gate.weight"] = sd[p + "block_sparse_moe.gate.weight"]
+        fused[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([sd[p + f"block_sparse_moe.experts.{e}.w1.weight"],
+                                                                        sd[p + f"block_sparse_moe.experts.{e}.w3.weight"]])
+                                                             for e in range(E)])
+        fused[p + "mlp.experts.down_proj"] = torch.stack([sd[p + f"block_sparse_moe.experts.{e}.w2.weight"] for e in range(E)])
+    save_checkpoint(cfg, sd, str(tmp_path / "classic"))
+    save_checkpoint(cfg, fused, str(tmp_path / "fused"))
+    a = load_safetensors_dir(ModelConfig.from_pretrained(str(tmp_path / "classic")), str(tmp_path / "classic"), 0, 1, "cpu")
+    b = load_safetensors_dir(ModelConfig.from_pretrained(str(tmp_path / "fused")), str(tmp_path / "fused"), 0, 1, "cpu")
+    for la, lb in zip(a.layers, b.layers):
+        assert torch.equal(la.router, lb.router) and torch.equal(la.w13, lb.w13) and torch.equal(la.w2, lb.w2)
