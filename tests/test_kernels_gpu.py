@@ -370,8 +370,8 @@ def test_moe_experts_vs_oracle(ops, T, E, K, H, I, out_dir):
     ws = ops.MoEWorkspace(T, K, E, H, I, "cuda")
     xc = x.cuda()
     logits = ops.gemm(xc, ops.pad_router(router.cuda()), out=ws.logits[:T])
-    assert torch.equal(logits[:, :E].cpu(), O.linear(x, router)) or \
-        float((logits[:, :E].cpu().float() - O.linear(x, router).float()).abs().max()) < 0.05
+    _close(logits[:, :E], O.linear(x, router), 1e-2, 1.6e-2, "router logits (padded one-tile GEMM)", out_dir)
+    assert not logits[:, E:].any()                                  # zero rows of the padded router weight
     w13 = torch.cat([ops.interleave_gate_up(w1[e], w3[e]) for e in range(E)]).cuda()
     w2s = torch.cat(w2).cuda()
     out = torch.empty(T, H, dtype=BF, device="cuda")
