@@ -209,6 +209,6 @@ extern "C" int b200_argmax_f32(const float* logits, int64_t ld, int32_t* out_idx
                                int B, int V, void* stream) {
   B200_REQUIRE(B >= 0 && V > 0, "argmax: bad shape");
   if (B == 0) return B200_OK;
-  (void)launch_pdl(argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx, out_val, V);
+  (void)launch_pdl_cls(kPdlSampler, argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx, out_val, V);
   return b200_check_launch("b200_argmax_f32");
 }

@@ -851,9 +851,9 @@ static int launch_gemm_grouped(const void* X, const void* W, void* Y, int M, int
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
   const int group_m = gemm_group_m(m_tiles);
-  cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
-                             tw, tx, Y, M, N, K, ldy, n_tiles, m_tiles, group_m, row_scale, tile_expert,
-                             num_m_tiles);
+  cudaError_t e = launch_pdl_cls(kPdlMoe, kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes,
+                                 stream, 2, tw, tx, Y, M, N, K, ldy, n_tiles, m_tiles, group_m, row_scale,
+                                 tile_expert, num_m_tiles);
   if (e != cudaSuccess) {
     b200_set_error("b200_moe_grouped_gemm: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

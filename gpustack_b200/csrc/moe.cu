@@ -181,7 +181,7 @@ extern "C" int b200_moe_route(const void* router_logits, int64_t ld, int32_t* to
   B200_REQUIRE(T >= 0 && E >= 1 && E <= kMaxExperts && K >= 1 && K <= kMaxTopK && K <= E,
                "moe_route: unsupported E=%d K=%d (E <= %d, K <= %d)", E, K, kMaxExperts, kMaxTopK);
   if (T == 0) return B200_OK;
-  (void)launch_pdl(moe_route_kernel, dim3((T + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1,
+  (void)launch_pdl_cls(kPdlMoe, moe_route_kernel, dim3((T + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1,
                    (const bf16*)router_logits, ld, topk_ids, topk_w, T, E, K, renormalize);
   return b200_check_launch("b200_moe_route");
 }
@@ -199,7 +199,7 @@ extern "C" int b200_moe_align(const int32_t* topk_ids, const float* topk_w, int 
   B200_REQUIRE(block_x >= 16 && block_x <= 256 && (block_x & (block_x - 1)) == 0, "moe_align: bad block_x=%d", block_x);
   B200_REQUIRE(capacity_rows >= b200_moe_capacity_rows(n_pairs, E, block_x),
                "moe_align: capacity_rows=%d too small for %d pairs", capacity_rows, n_pairs);
-  (void)launch_pdl(moe_align_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 1, topk_ids, topk_w, n_pairs, E,
+  (void)launch_pdl_cls(kPdlMoe, moe_align_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 1, topk_ids, topk_w, n_pairs, E,
                    block_x, capacity_rows, pair_row, row_pair, row_weight, tile_expert, num_tiles);
   return b200_check_launch("b200_moe_align");
 }
@@ -209,7 +209,7 @@ extern "C" int b200_moe_gather(const void* x, const int32_t* row_pair, const int
   B200_REQUIRE(H > 0 && H % 8 == 0 && K >= 1, "moe_gather: H=%d must be a multiple of 8", H);
   if (capacity_rows == 0) return B200_OK;
   const size_t items = (size_t)capacity_rows * (H / 8);
-  (void)launch_pdl(moe_gather_kernel, dim3(moe_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
+  (void)launch_pdl_cls(kPdlMoe, moe_gather_kernel, dim3(moe_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
                    (const bf16*)x, row_pair, num_tiles, (bf16*)xp, H, K, capacity_rows);
   return b200_check_launch("b200_moe_gather");
 }
@@ -219,7 +219,7 @@ extern "C" int b200_moe_combine(const void* yp, const int32_t* pair_row, void* o
   B200_REQUIRE(H > 0 && H % 8 == 0 && K >= 1, "moe_combine: H=%d must be a multiple of 8", H);
   if (T == 0) return B200_OK;
   const size_t items = (size_t)T * (H / 8);
-  (void)launch_pdl(moe_combine_kernel, dim3(moe_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
+  (void)launch_pdl_cls(kPdlMoe, moe_combine_kernel, dim3(moe_grid(items, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
                    (const bf16*)yp, pair_row, (bf16*)out, T, H, K);
   return b200_check_launch("b200_moe_combine");
 }

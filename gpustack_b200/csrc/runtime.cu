@@ -60,6 +60,20 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+bool pdl_class_enabled(int cls) {
+  static int off = -1;
+  if (off < 0) {
+    // Default: the MoE routing kernels and grouped GEMMs are launched fully serialised.  Measured on
+    // B200 (tools/debug_moe_graph.py): with them launched as programmatic dependents, CUDA-graph
+    // replays of the tiny Mixtral decode step hand the host stale sampled tokens, deterministically
+    // (eager launches, and graphs with this class serialised, are correct; so are the dense graphs).
+    // Their successors still overlap with them; B200_PDL_OFF_CLASSES=0 re-enables for experiments.
+    const char* e = getenv("B200_PDL_OFF_CLASSES");
+    off = e ? atoi(e) : (int)kPdlMoe;
+  }
+  return cls == 0 || (off & cls) == 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

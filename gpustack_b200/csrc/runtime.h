@@ -27,10 +27,15 @@ int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 // B200_PDL=0 disables programmatic dependent launch (default on).
 bool pdl_enabled();
 
+// Kernel classes whose launches can be taken out of programmatic dependent launch individually
+// (B200_PDL_OFF_CLASSES = bitmask, default 2): 1 = step-final sampler, 2 = MoE routing / grouped GEMMs.
+enum PdlClass { kPdlDefault = 0, kPdlSampler = 1, kPdlMoe = 2 };
+bool pdl_class_enabled(int cls);
+
 // Launch with the programmatic-stream-serialization attribute (and an optional cluster size).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, int cluster, Args&&... args) {
+inline cudaError_t launch_pdl_cls(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t stream, int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -38,7 +43,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled() && pdl_class_enabled(cls)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -53,6 +58,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, int cluster, Args&&... args) {
+  return launch_pdl_cls(kPdlDefault, kernel, grid, block, smem, stream, cluster, static_cast<Args&&>(args)...);
 }
 
 }  // namespace b200
