@@ -46,6 +46,15 @@ def build_parser() -> argparse.ArgumentParser:
     s.add_argument("--quantization", "-q", default=None, choices=[None, "fp8"])
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
+    est = sub.add_parser("estimate", help="print the engine's exact VRAM requirement (GPUSTACK_MODEL_VRAM_CLAIM)")
+    est.add_argument("model", help="model directory (config.json) or random:<llama3-8b|tiny>")
+    est.add_argument("--tensor-parallel-size", "-tp", type=int, default=1)
+    est.add_argument("--max-model-len", type=int, default=None)
+    est.add_argument("--max-num-seqs", type=int, default=256)
+    est.add_argument("--max-num-batched-tokens", type=int, default=8192)
+    est.add_argument("--gpu-memory-utilization", type=float, default=0.90)
+    est.add_argument("--quantization", "-q", default=None, choices=[None, "fp8"])
+    est.add_argument("--kv-tokens", type=int, default=None, help="KV-cache capacity to size the claim for")
     w = sub.add_parser("_worker", help=argparse.SUPPRESS)
     w.add_argument("--engine-json", required=True)
     return p
@@ -98,6 +107,23 @@ def main(argv: Optional[List[str]] = None) -> int:
     args, unknown = build_parser().parse_known_args(argv)
     logging.basicConfig(level=getattr(logging, getattr(args, "log_level", "info").upper(), logging.INFO),
                         format="%(asctime)s %(levelname)s %(name)s: %(message)s")
+    if args.cmd == "estimate":
+        import json
+
+        from .config import EngineConfig, ModelConfig, llama3_8b, tiny_llama
+        from .resource_fit import estimate
+
+        if args.model.startswith("random:"):
+            mcfg, disk = (llama3_8b() if "8b" in args.model else tiny_llama()), None
+        else:
+            mcfg = ModelConfig.from_pretrained(args.model)
+            disk = sum(f.stat().st_size for f in __import__("pathlib").Path(args.model).glob("*.safetensors")) or None
+        ecfg = EngineConfig(model=args.model, tensor_parallel_size=args.tensor_parallel_size,
+                            max_model_len=args.max_model_len, max_num_seqs=args.max_num_seqs,
+                            max_num_batched_tokens=args.max_num_batched_tokens,
+                            gpu_memory_utilization=args.gpu_memory_utilization, quantization=args.quantization)
+        print(json.dumps(estimate(mcfg, ecfg, weights_on_disk=disk, kv_tokens=args.kv_tokens).to_dict(), indent=1))
+        return 0
     if args.cmd == "_worker":
         import json
 

@@ -185,8 +185,8 @@ def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank:
     V = cfg.vocab_size
     per = (V + tp - 1) // tp
     v0, v1 = rank * per, min(V, (rank + 1) * per)
-    lm_full = embed if cfg.tie_word_embeddings else get("lm_head.weight")
-    lm = dev(lm_full[v0:v1]) if (tp > 1 or not cfg.tie_word_embeddings) else embed
+    # tied embeddings: the vocab shard is a row-range VIEW of the replicated table (no second copy)
+    lm = embed[v0:v1] if cfg.tie_word_embeddings else dev(get("lm_head.weight")[v0:v1])
     return ModelWeights(embed=embed, layers=layers, final_norm=dev(get("model.norm.weight")),
                         lm_head=lm, vocab_start=v0, vocab_end=v1)
 

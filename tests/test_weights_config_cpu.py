@@ -62,6 +62,9 @@ def test_tied_embeddings_share_storage_on_one_gpu():
     assert "lm_head.weight" not in sd
     w = shard_state_dict(cfg, lambda k: sd[k], 0, 1, "cpu")
     assert w.lm_head.data_ptr() == w.embed.data_ptr()
+    w1 = shard_state_dict(cfg, lambda k: sd[k], 1, 2, "cpu")       # TP: a row-range view, still no copy
+    assert w1.lm_head.untyped_storage().data_ptr() == w1.embed.untyped_storage().data_ptr()
+    assert torch.equal(w1.lm_head, sd["model.embed_tokens.weight"][w1.vocab_start:w1.vocab_end])
 
 
 def test_checkpoint_round_trip(tmp_path):
@@ -275,3 +278,49 @@ def test_mixtral_config_and_transformers5_fused_checkpoint_layout(tmp_path):
     b = load_safetensors_dir(ModelConfig.from_pretrained(str(tmp_path / "fused")), str(tmp_path / "fused"), 0, 1, "cpu")
     for la, lb in zip(a.layers, b.layers):
         assert torch.equal(la.router, lb.router) and torch.equal(la.w13, lb.w13) and torch.equal(la.w2, lb.w2)
+
+
+# --------------------------------------------------------------------- VRAM model
+def _resident_bytes(w):
+    """bytes the shard occupies once every tensor is its own device buffer (on the CPU the row
+    slices are views of the full checkpoint tensors); a tied lm_head is a view of the embedding."""
+    tensors = [w.embed, w.final_norm]
+    if w.lm_head.untyped_storage().data_ptr() != w.embed.untyped_storage().data_ptr():
+        tensors.append(w.lm_head)
+    for lw in w.layers:
+        tensors += [t for t in vars(lw).values() if isinstance(t, torch.Tensor)]
+    return sum(t.numel() * t.element_size() for t in tensors)
+
+
+@pytest.mark.parametrize("kind", ["llama", "qwen2-bias-tied", "mixtral", "fp8"])
+@pytest.mark.parametrize("tp", [1, 2])
+def test_vram_model_weight_bytes_equal_the_loaded_shards(kind, tp):
+    from gpustack_b200.config import tiny_mixtral
+    from gpustack_b200.resource_fit import weight_bytes_per_gpu
+
+    cfg = {"llama": _cfg(), "qwen2-bias-tied": _cfg(bias=True, tie=True), "mixtral": tiny_mixtral(), "fp8": _cfg()}[kind]
+    quant = "fp8" if kind == "fp8" else None
+    sd = random_state_dict(cfg, seed=11, device="cpu")
+    for rank in range(tp):
+        w = shard_state_dict(cfg, lambda k: sd[k], rank, tp, "cpu", quantization=quant, has=lambda k: k in sd)
+        assert weight_bytes_per_gpu(cfg, tp, quant) == _resident_bytes(w)
+
+
+def test_vram_estimate_and_cli(capsys):
+    from gpustack_b200.cli import main
+    from gpustack_b200.resource_fit import GiB, estimate
+
+    m = llama3_8b()
+    e1 = estimate(m, EngineConfig(max_model_len=8192))
+    assert e1.weights == 16_060_522_496 and e1.kv_tokens == 8192 and e1.kv_bytes_per_token == 131_072
+    assert e1.total_min == e1.per_gpu_min and 20 * GiB < e1.total_min < 22 * GiB
+    assert e1.env() == {"GPUSTACK_MODEL_VRAM_CLAIM": str(e1.total_min)}
+    assert e1.reference_heuristic == int(16_060_522_496 * 1.2) + 2 * GiB          # GPUStack's own formula
+    e8 = estimate(m, EngineConfig(max_model_len=8192, tensor_parallel_size=8), kv_tokens=1_000_000)
+    assert e8.kv_bytes_per_token == 16_384 and e8.total_min == 8 * e8.per_gpu_min
+    assert e8.kv_cache_requested >= 1_000_000 * 16_384 and e8.weights < e1.weights / 4
+    f8 = estimate(m, EngineConfig(max_model_len=8192, quantization="fp8"))
+    assert f8.weights < 0.6 * e1.weights
+    assert main(["estimate", "random:llama3-8b", "--max-model-len", "8192", "--kv-tokens", "500000"]) == 0
+    out = json.loads(capsys.readouterr().out)
+    assert out["kv_tokens"] == 500000 and int(out["env"]["GPUSTACK_MODEL_VRAM_CLAIM"]) == out["total_min"]
