@@ -48,7 +48,9 @@ def parse_args():
     ap.add_argument("--requests", type=int, default=256, help="requests per step (= concurrency)")
     ap.add_argument("--input-len", type=int, default=512)
     ap.add_argument("--output-len", type=int, default=128)
-    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tiny", "tiny128"])
+    ap.add_argument("--model", default="llama3-8b",
+                    choices=["llama3-8b", "tiny", "tiny128", "mixtral-8x7b", "tiny-mixtral"],
+                    help="llama3-8b is the BASELINE config; mixtral-8x7b is a side measurement of the MoE family")
     ap.add_argument("--max-num-batched-tokens", type=int, default=8192, help="prefill token budget per engine step")
     ap.add_argument("--quantization", default=None, choices=[None, "fp8"],
                     help="fp8 = W8A8 side measurement (NOT the BASELINE config, which is bf16)")
@@ -82,9 +84,10 @@ def host_threads() -> int:
 
 
 def model_config(name):
-    from gpustack_b200.config import llama3_8b, tiny_llama
+    from gpustack_b200.config import llama3_8b, mixtral_8x7b, tiny_llama, tiny_mixtral
 
-    return {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128)}[name]()
+    return {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128),
+            "mixtral-8x7b": mixtral_8x7b, "tiny-mixtral": tiny_mixtral}[name]()
 
 
 def workload(step, R, in_len, vocab):

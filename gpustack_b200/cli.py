@@ -23,7 +23,7 @@ from typing import List, Optional
 
 log = logging.getLogger("b200-engine")
 
-RANDOM_MODELS = ("random:llama3-8b", "random:tiny", "random:tiny128")
+RANDOM_MODELS = ("random:llama3-8b", "random:tiny", "random:tiny128", "random:mixtral-8x7b", "random:tiny-mixtral")
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -79,12 +79,13 @@ def _engine_config(args, tp: int):
 
 
 def make_engine(ecfg):
-    from .config import llama3_8b, tiny_llama
+    from .config import llama3_8b, mixtral_8x7b, tiny_llama, tiny_mixtral
     from .engine import LLMEngine
 
     if ecfg.model.startswith("random:"):
         name = ecfg.model.split(":", 1)[1]
-        mcfg = {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128)}[name]()
+        mcfg = {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128),
+                "mixtral-8x7b": mixtral_8x7b, "tiny-mixtral": tiny_mixtral}[name]()
         return LLMEngine.from_engine_config(ecfg, mcfg=mcfg)
     return LLMEngine.from_engine_config(ecfg)
 

@@ -20,7 +20,8 @@ from .config import EngineConfig, ModelConfig
 from .lib import B200Error
 from .runner import ModelRunner
 from .scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
-from .weights import ModelWeights, load_safetensors_dir, random_state_dict, shard_state_dict
+from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, random_state_dict,
+                      shard_state_dict)
 
 log = logging.getLogger("b200.engine")
 
@@ -208,6 +209,13 @@ class LLMEngine:
             quant = ecfg.quantization or mcfg.quantization      # CLI flag, else the checkpoint's own config
             weights = load_safetensors_dir(mcfg, ecfg.model, rank, ecfg.tensor_parallel_size, device,
                                            quantization=quant)
+        elif state_dict is None and mcfg.num_local_experts:
+            # mixture-of-experts shapes are too large to hold the synthetic checkpoint and its fused
+            # shards at the same time: synthesise tensor by tensor
+            get, has = lazy_random_source(mcfg, seed=ecfg.seed, device=device)
+            weights = shard_state_dict(mcfg, get, rank, ecfg.tensor_parallel_size, device,
+                                       quantization=ecfg.quantization or mcfg.quantization, has=has)
+            torch.cuda.empty_cache()
         else:
             if state_dict is None:
                 state_dict = random_state_dict(mcfg, seed=ecfg.seed, device=device)

@@ -257,6 +257,49 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, std: float = 0.02, device
     return w
 
 
+def lazy_random_source(cfg: ModelConfig, seed: int = 0, std: float = 0.02, device: str = "cuda"):
+    """(get, has) for shard_state_dict that synthesise each checkpoint tensor on demand instead of
+    materialising the whole state dict first -- a 47 B-parameter Mixtral would otherwise be resident
+    twice while its shards are fused.  Every tensor is N(0, std) (router 10x wider, norms 1 + N(0, 0.1))
+    from a generator seeded by a hash of (seed, name), so any rank / any call order sees the same values."""
+    import zlib
+
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    shapes: Dict[str, tuple] = {"model.embed_tokens.weight": (cfg.vocab_size, H), "model.norm.weight": (H,)}
+    if not cfg.tie_word_embeddings:
+        shapes["lm_head.weight"] = (cfg.vocab_size, H)
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        shapes[p + "input_layernorm.weight"] = (H,)
+        shapes[p + "post_attention_layernorm.weight"] = (H,)
+        for n, rows in (("q", cfg.q_size), ("k", cfg.kv_size), ("v", cfg.kv_size)):
+            shapes[p + f"self_attn.{n}_proj.weight"] = (rows, H)
+            if cfg.attention_bias:
+                shapes[p + f"self_attn.{n}_proj.bias"] = (rows,)
+        shapes[p + "self_attn.o_proj.weight"] = (H, cfg.q_size)
+        if cfg.num_local_experts:
+            shapes[p + "block_sparse_moe.gate.weight"] = (cfg.num_local_experts, H)
+            for e in range(cfg.num_local_experts):
+                shapes[p + f"block_sparse_moe.experts.{e}.w1.weight"] = (I, H)
+                shapes[p + f"block_sparse_moe.experts.{e}.w3.weight"] = (I, H)
+                shapes[p + f"block_sparse_moe.experts.{e}.w2.weight"] = (H, I)
+        else:
+            shapes[p + "mlp.gate_proj.weight"] = (I, H)
+            shapes[p + "mlp.up_proj.weight"] = (I, H)
+            shapes[p + "mlp.down_proj.weight"] = (H, I)
+
+    def get(name: str) -> torch.Tensor:
+        g = torch.Generator(device=device)
+        g.manual_seed(zlib.crc32(f"{seed}/{name}".encode()) | (zlib.crc32(f"{name}#{seed}".encode()) << 32))
+        shape = shapes[name]
+        x = torch.randn(*shape, generator=g, device=device, dtype=torch.float32)
+        if name.endswith("norm.weight"):
+            return (1.0 + x * 0.1).to(BF16)
+        return (x * (10 * std if name.endswith("block_sparse_moe.gate.weight") else std)).to(BF16)
+
+    return get, (lambda name: name in shapes)
+
+
 def save_checkpoint(cfg: ModelConfig, state: Dict[str, torch.Tensor], out_dir: str, shard_bytes: int = 4 << 30) -> None:
     """Write an HF-format directory (config.json + sharded safetensors + index) so that the same
     synthetic weights can be served by this engine and by the reference's vLLM backend."""

@@ -324,3 +324,22 @@ def test_vram_estimate_and_cli(capsys):
     assert main(["estimate", "random:llama3-8b", "--max-model-len", "8192", "--kv-tokens", "500000"]) == 0
     out = json.loads(capsys.readouterr().out)
     assert out["kv_tokens"] == 500000 and int(out["env"]["GPUSTACK_MODEL_VRAM_CLAIM"]) == out["total_min"]
+
+
+def test_lazy_random_source_is_deterministic_and_complete():
+    from gpustack_b200.config import tiny_mixtral
+    from gpustack_b200.weights import lazy_random_source
+
+    for cfg in (tiny_mixtral(), _cfg(bias=True, tie=True)):
+        get, has = lazy_random_source(cfg, seed=3, device="cpu")
+        w = shard_state_dict(cfg, get, 0, 1, "cpu", has=has)
+        get2, has2 = lazy_random_source(cfg, seed=3, device="cpu")
+        w2 = shard_state_dict(cfg, get2, 0, 1, "cpu", has=has2)
+        assert torch.equal(w.layers[1].qkv, w2.layers[1].qkv) and torch.equal(w.embed, w2.embed)
+        assert not has("model.layers.0.self_attn.q_proj.weight_scale")
+        get3, _ = lazy_random_source(cfg, seed=4, device="cpu")
+        assert not torch.equal(get("model.norm.weight"), get3("model.norm.weight"))
+        assert abs(float(get("model.norm.weight").float().mean()) - 1.0) < 0.1
+        if cfg.num_local_experts:
+            assert w.layers[0].w13.shape[0] == cfg.num_local_experts * 2 * cfg.intermediate_size
+            assert float(w.layers[0].router[:8].float().std()) > 5 * float(w.layers[0].w2.float().std())
