@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--input-len", type=int, default=512)
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--model", default="llama3-8b",
-                    choices=["llama3-8b", "tiny", "tiny128", "mixtral-8x7b", "tiny-mixtral"],
+                    choices=["llama3-8b", "llama3-70b", "tiny", "tiny128", "mixtral-8x7b", "tiny-mixtral"],
                     help="llama3-8b is the BASELINE config; mixtral-8x7b is a side measurement of the MoE family")
     ap.add_argument("--max-num-batched-tokens", type=int, default=8192, help="prefill token budget per engine step")
     ap.add_argument("--quantization", default=None, choices=[None, "fp8"],
@@ -84,9 +84,9 @@ def host_threads() -> int:
 
 
 def model_config(name):
-    from gpustack_b200.config import llama3_8b, mixtral_8x7b, tiny_llama, tiny_mixtral
+    from gpustack_b200.config import llama3_8b, llama3_70b, mixtral_8x7b, tiny_llama, tiny_mixtral
 
-    return {"llama3-8b": llama3_8b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128),
+    return {"llama3-8b": llama3_8b, "llama3-70b": llama3_70b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128),
             "mixtral-8x7b": mixtral_8x7b, "tiny-mixtral": tiny_mixtral}[name]()
 
 
@@ -365,7 +365,8 @@ def run_ours(a):
         "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if a.quantization is None else "fp8 e4m3 W8A8 linears, bf16 elsewhere", "data": "synthetic",
         "config": {"workload": f"Llama-3-8B {'bf16' if a.quantization is None else 'fp8-W8A8'} TP={a.gpus}, continuous batching, {a.input_len}-in/{a.output_len}-out greedy"
-                   if a.model == "llama3-8b" else f"{a.model} TP={a.gpus} {a.input_len}-in/{a.output_len}-out",
+                   if a.model == "llama3-8b" else
+                   f"{a.model} {'bf16' if a.quantization is None else 'fp8-W8A8'} TP={a.gpus} {a.input_len}-in/{a.output_len}-out",
                    "requests_per_step": R, "concurrency": R, "weights": "seeded N(0,0.02) random init",
                    "prompts": "seeded uniform token ids, fresh per step (working set 16 GB weights >> 126 MB L2)",
                    "parallelism": f"tp{a.gpus}", "max_num_batched_tokens": a.max_num_batched_tokens,

@@ -137,6 +137,13 @@ def llama3_8b() -> ModelConfig:
                        bos_token_id=128000)
 
 
+def llama3_70b() -> ModelConfig:
+    return ModelConfig(vocab_size=128256, hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
+                       num_attention_heads=64, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
+                       rope_theta=500000.0, max_position_embeddings=8192, eos_token_id=128001,
+                       bos_token_id=128000)
+
+
 def tiny_mixtral() -> ModelConfig:
     return ModelConfig(vocab_size=512, hidden_size=512, intermediate_size=256, num_hidden_layers=2,
                        num_attention_heads=8, num_key_value_heads=2, head_dim=64, rope_theta=1e6,

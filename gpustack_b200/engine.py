@@ -209,9 +209,9 @@ class LLMEngine:
             quant = ecfg.quantization or mcfg.quantization      # CLI flag, else the checkpoint's own config
             weights = load_safetensors_dir(mcfg, ecfg.model, rank, ecfg.tensor_parallel_size, device,
                                            quantization=quant)
-        elif state_dict is None and mcfg.num_local_experts:
-            # mixture-of-experts shapes are too large to hold the synthetic checkpoint and its fused
-            # shards at the same time: synthesise tensor by tensor
+        elif state_dict is None and (mcfg.num_local_experts or mcfg.weight_bytes(1) > 48e9):
+            # mixture-of-experts / 70B shapes are too large to hold the synthetic checkpoint and its
+            # fused shards at the same time: synthesise tensor by tensor
             get, has = lazy_random_source(mcfg, seed=ecfg.seed, device=device)
             weights = shard_state_dict(mcfg, get, rank, ecfg.tensor_parallel_size, device,
                                        quantization=ecfg.quantization or mcfg.quantization, has=has)

@@ -434,6 +434,8 @@ def _make_paged(g, seq_lens, Hkv, D, extra_blocks=5):
     (14, 2, 64, [900, 31], 3),
     (4, 1, 128, [8192], 16),
     (8, 8, 128, [50, 130], 1),
+    (64, 8, 128, [300, 17, 2049], 1),                     # Llama-3-70B heads: group of 8
+    (16, 2, 128, [4100, 640], 4),
 ])
 def test_paged_attn_decode(ops, Hq, Hkv, D, seq_lens, splits, out_dir):
     g = torch.Generator().manual_seed(sum(seq_lens))
