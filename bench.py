@@ -352,7 +352,7 @@ def run_ours(a):
     dsteps = st1["decode_steps"] - st0["decode_steps"]
     dtime = stime1["decode"] - stime0["decode"]
     kv_tok = st1["decode_kv_tokens"] - st0["decode_kv_tokens"]
-    dbytes = dsteps * mcfg.weight_bytes(a.gpus) + kv_tok * mcfg.kv_bytes_per_token(a.gpus)
+    dbytes = dsteps * mcfg.weight_bytes(a.gpus, a.quantization) + kv_tok * mcfg.kv_bytes_per_token(a.gpus)
     dgbs = dbytes / dtime / 1e9 if dtime else 0.0
     decode_roof = {"bound": "hbm", "achieved": dgbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": dgbs / pk["hbm_gbs"], "steps": dsteps, "ms_per_decode_step": dtime / max(1, dsteps) * 1e3,

@@ -49,13 +49,16 @@ class ModelConfig:
     def kv_bytes_per_token(self, tp: int = 1) -> int:
         return 2 * self.num_hidden_layers * (self.num_key_value_heads // tp) * self.head_dim * 2
 
-    def weight_bytes(self, tp: int = 1) -> int:
-        """bf16 bytes streamed per decode step on one rank (layers + lm_head + final norm)."""
+    def weight_bytes(self, tp: int = 1, quantization: Optional[str] = None) -> int:
+        """bytes streamed per decode step on one rank (layers + lm_head + norms); the decoder linears
+        are 1 byte/parameter under fp8, lm_head and norms stay bf16."""
         H, I = self.hidden_size, self.intermediate_size
-        mlp = 3 * I * H * max(1, self.num_local_experts) + self.num_local_experts * H * tp   # all experts hot
+        lin_b = 1 if (quantization or self.quantization) == "fp8" else 2
+        mlp = 3 * I * H * max(1, self.num_local_experts)                      # all experts hot
         per_layer = (self.q_size + 2 * self.kv_size) * H + self.q_size * H + mlp
-        norms = (2 * self.num_hidden_layers + 1) * H          # replicated
-        return 2 * (self.num_hidden_layers * per_layer // tp + self.vocab_size * H // tp + norms)
+        router = self.num_local_experts * H * 2 * self.num_hidden_layers      # replicated, bf16
+        norms = (2 * self.num_hidden_layers + 1) * H * 2                      # replicated
+        return self.num_hidden_layers * per_layer // tp * lin_b + self.vocab_size * H // tp * 2 + norms + router
 
     @staticmethod
     def from_dict(d: dict) -> "ModelConfig":
