@@ -65,8 +65,9 @@ bool pdl_class_enabled(int cls) {
   if (off < 0) {
     // Default: the MoE routing kernels and grouped GEMMs are launched fully serialised.  Measured on
     // B200 (tools/debug_moe_graph.py): with them launched as programmatic dependents, CUDA-graph
-    // replays of the tiny Mixtral decode step hand the host stale sampled tokens, deterministically
-    // (eager launches, and graphs with this class serialised, are correct; so are the dense graphs).
+    // replays of the tiny Mixtral decode step compute different logits for one sequence from the
+    // second decode step on, deterministically (eager launches, and graphs with this class
+    // serialised, are correct; so are the dense graphs) -- see DESIGN.md section 9.
     // Their successors still overlap with them; B200_PDL_OFF_CLASSES=0 re-enables for experiments.
     const char* e = getenv("B200_PDL_OFF_CLASSES");
     off = e ? atoi(e) : (int)kPdlMoe;

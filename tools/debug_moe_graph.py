@@ -49,17 +49,25 @@ def run(mode: str):
         eng.add_request(f"r{i}", p, sp)
     toks = {f"r{i}": [] for i in range(5)}
     logits1 = None
+    diag = []
     step = 0
     while eng.sched.has_work():
         out = eng.step()
         for rid, t in zip(out.req_ids, out.token_ids):
             toks[rid].append(int(t))
+        if step >= 1 and step <= 3:
+            torch.cuda.synchronize()
+            n = len(out.req_ids)
+            dev_ids = eng.runner.out_ids[:n].cpu().tolist()            # device copy of the sampler output, after a full sync
+            host_arg = eng.runner.last_logits(n).float().cpu().argmax(dim=-1).tolist()
+            diag.append({"step": step, "returned": [int(t) for t in out.token_ids], "out_ids_after_sync": dev_ids,
+                         "argmax_of_logits": host_arg})
         if step == 1:
             lg = eng.runner.last_logits(5).float().cpu()
             logits1 = [[round(float(x), 4) for x in row[:6]] + [float(row.abs().max()), bool(torch.isnan(row).any())]
                        for row in lg]
         step += 1
-    print("RESULT " + json.dumps({"mode": ("dense-" if dense else "") + mode, "tokens": toks, "logits_step1": logits1}))
+    print("RESULT " + json.dumps({"mode": ("dense-" if dense else "") + mode, "tokens": toks, "logits_step1": logits1, "diag": diag}))
 
 
 if __name__ == "__main__":
@@ -67,10 +75,7 @@ if __name__ == "__main__":
         run(sys.argv[1])
         sys.exit(0)
     res = {}
-    for mode, env in (("eager", {}), ("graph8", {}), ("graph8-all-pdl", {"B200_PDL_OFF_CLASSES": "0"}),
-                      ("graph8-sampler-serial", {"B200_PDL_OFF_CLASSES": "1"}),
-                      ("graph8-both-serial", {"B200_PDL_OFF_CLASSES": "3"}),
-                      ("dense-eager", {}), ("dense-graph8", {})):
+    for mode, env in (("eager", {}), ("graph8-all-pdl", {"B200_PDL_OFF_CLASSES": "0"}), ("graph8", {})):
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, __file__, mode], capture_output=True, text=True, env=e, timeout=300)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
@@ -84,3 +89,5 @@ if __name__ == "__main__":
         print(mode, "tokens_equal_eager=", same)
         if not same:
             print("   tokens", r["tokens"])
+        for d in r.get("diag", []):
+            print("   ", d)
