@@ -29,3 +29,17 @@ def test_tp_engine_matches_oracle(world, eager, allreduce):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER=eager, B200_TP_ALLREDUCE=allreduce))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout
+
+
+@pytest.mark.parametrize("family", ["fp8", "mixtral"])
+@pytest.mark.parametrize("eager", ["1", "0"])
+def test_tp2_fp8_and_mixtral_families(family, eager):
+    """W8A8 shards quantised per rank, and Mixtral experts tensor-parallel over I, at TP=2."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, TP_EAGER=eager, TP_FAMILY=family))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout

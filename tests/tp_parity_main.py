@@ -1,6 +1,8 @@
 """Tensor-parallel parity check, launched with torch.distributed.run (one rank per GPU) by
 tests/test_tp_gpu.py:  the TP engine must reproduce the CPU oracle's logits (stated tolerance
-2e-2 * max|logit|) and the single-GPU engine's greedy tokens."""
+2e-2 * max|logit|) and the single-GPU engine's greedy tokens.  TP_FAMILY selects the model family:
+dense (default), fp8 (W8A8; every rank quantises its own shard, tolerance 0.12 as in
+tests/test_engine_gpu.py) or mixtral (experts tensor-parallel over I, tolerance 5e-2)."""
 import json
 import os
 import sys
@@ -19,26 +21,32 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    c = O.LlamaConfig(vocab_size=1000, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
-                      num_attention_heads=8, num_key_value_heads=world if world <= 8 else 8, head_dim=64,
-                      max_position_embeddings=512)
+    family = os.environ.get("TP_FAMILY", "dense")
+    tol = {"dense": 2e-2, "fp8": 0.12, "mixtral": 5e-2}[family]
+    moe = dict(num_local_experts=8, num_experts_per_tok=2) if family == "mixtral" else {}
+    c = O.LlamaConfig(vocab_size=1000, hidden_size=512, intermediate_size=256 * world if family == "mixtral" else 1024,
+                      num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=world if world <= 8 else 8,
+                      head_dim=64, max_position_embeddings=512, **moe)
     if c.num_attention_heads % c.num_key_value_heads:
         c.num_attention_heads = c.num_key_value_heads * 2
     mcfg = ModelConfig(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
                        num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
                        num_key_value_heads=c.num_key_value_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
-                       max_position_embeddings=c.max_position_embeddings, eos_token_id=2)
+                       max_position_embeddings=c.max_position_embeddings, eos_token_id=2,
+                       num_local_experts=c.num_local_experts, num_experts_per_tok=c.num_experts_per_tok,
+                       architecture="MixtralForCausalLM" if c.num_local_experts else "LlamaForCausalLM")
     weights = O.init_weights(c, seed=21)
     ecfg = EngineConfig(tensor_parallel_size=world, max_num_seqs=8, max_num_batched_tokens=128, num_gpu_blocks=128,
-                        cuda_graph_sizes=[1, 2, 4, 8], enforce_eager=os.environ.get("TP_EAGER", "0") == "1")
+                        cuda_graph_sizes=[1, 2, 4, 8], enforce_eager=os.environ.get("TP_EAGER", "0") == "1",
+                        quantization="fp8" if family == "fp8" else None)
     eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
     if rank != 0:
         TPWorker(eng).serve_forever()
         return
     g = torch.Generator().manual_seed(4)
     prompts = [torch.randint(3, c.vocab_size, (n,), generator=g).tolist() for n in (9, 40, 77, 130)]
-    oracle = O.OracleLlama(c, weights)
-    res = {"world": world, "ok": True, "checks": []}
+    oracle = O.OracleLlama(c, weights, quantization=ecfg.quantization)
+    res = {"world": world, "family": family, "ok": True, "checks": []}
     outs = eng.generate(prompts, SamplingParams(max_tokens=12, ignore_eos=True))
     for i, (p, o) in enumerate(zip(prompts, outs)):
         oracle.reset()
@@ -46,12 +54,12 @@ def main():
         n_ok = n_chk = 0
         for t in range(len(o)):
             top2 = torch.topk(logits, 2).values
-            if float(top2[0] - top2[1]) > 2e-2 * float(logits.abs().max()):
+            if float(top2[0] - top2[1]) > tol * float(logits.abs().max()):
                 n_chk += 1
                 n_ok += int(int(torch.argmax(logits)) == o[t])
             logits = oracle.forward(i, [o[t]])[-1]
         res["checks"].append({"seq": i, "checked": n_chk, "agree": n_ok})
-        if n_ok != n_chk or n_chk < 3:
+        if n_ok != n_chk or n_chk < (3 if family == "dense" else 1):
             res["ok"] = False
     eng.shutdown()
     print("TP_PARITY " + json.dumps(res), flush=True)
