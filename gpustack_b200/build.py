@@ -51,22 +51,26 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> Path:
+    """variant "" = the product library; "late" = libb200_late.so, the experimental build whose kernels
+    release their programmatic dependents only after their own dependency wait (-DB200_PDL_LATE_TRIGGER)."""
     srcs = [CSRC / s for s in SOURCES]
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [
         CSRC.parent.parent / "include" / "b200.h"
     ]
-    stamp = CSRC / "build" / "stamp"
-    digest = _digest(deps)
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
-        return LIB
+    lib = LIB if not variant else CSRC / f"libb200_{variant}.so"
+    extra = {"": [], "late": ["-DB200_PDL_LATE_TRIGGER=1"]}[variant]
+    objdir = CSRC / ("build" if not variant else f"build_{variant}")
+    stamp = objdir / "stamp"
+    digest = _digest(deps) + variant
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == digest:
+        return lib
     nvcc = _nvcc()
-    objdir = CSRC / "build"
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src: Path):
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = objdir / (src.stem + ".log")
         log.write_text(r.stdout + r.stderr)
@@ -78,13 +82,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-o", str(lib), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, variant="late" if "--late" in sys.argv else ""))

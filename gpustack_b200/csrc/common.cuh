@@ -94,10 +94,20 @@ __device__ __forceinline__ float warp_max(float v) {
 // Every kernel starts with pdl_launch_dependents() (the next kernel in the stream may be scheduled
 // and run its prologue while this one is still executing) and calls pdl_wait() before its first
 // global-memory access (blocks until the preceding kernel has completed and flushed).
+#ifdef B200_PDL_LATE_TRIGGER
+// Experimental variant (libb200_late.so, tools/debug_moe_graph.py): dependents are released only
+// AFTER this kernel's own dependency wait, so at most two kernels of a chain are resident at once.
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#else
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------ clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {

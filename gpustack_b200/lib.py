@@ -6,6 +6,7 @@ or a call returns an error, a B200Error is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 
@@ -69,7 +70,9 @@ SIGNATURES = {
 
 
 def lib_path() -> Path:
-    return _build.LIB
+    # B200_LIB selects an experimental build of the same ABI (e.g. csrc/libb200_late.so)
+    override = os.environ.get("B200_LIB")
+    return Path(override) if override else _build.LIB
 
 
 def load(build_if_missing: bool = True):
