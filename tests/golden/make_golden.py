@@ -7,7 +7,8 @@ Sources of truth imported here (never at test time on the GPU box):
     fused_add_rms_norm}, RotaryEmbedding.forward_static (neox), SiluAndMul.forward_native;
   * HF transformers LlamaForCausalLM (eager attention) for whole-model logits and greedy tokens
     of the seeded tiny Llama configs.
-Outputs: tests/golden/ops_vllm.pt, fp8_quant_vllm.pt, tiny_llama_hf.pt, tiny_qwen2_hf.pt (a few hundred KB).
+Outputs: tests/golden/ops_vllm.pt, fp8_quant_vllm.pt, fp8_linear_vllm.pt, tiny_llama_hf.pt, tiny_qwen2_hf.pt,
+tiny_mixtral_hf.pt (a few hundred KB).
 """
 import sys
 from pathlib import Path
@@ -78,6 +79,29 @@ def fp8_quant_from_vllm():
         out[f"scale_{key}"] = scale.clone()
     torch.save(out, OUT / "fp8_quant_vllm.pt")
     print("wrote fp8_quant_vllm.pt")
+
+
+def fp8_linear_from_vllm():
+    """The W8A8 linear as the reference engine's pure-PyTorch fallback computes it
+    (ChannelWiseTorchFP8ScaledMMLinearKernel.apply_scaled_mm: torch._scaled_mm of the e4m3 codes
+    with unit scales in fp32, then * x_scale * w_scale (+ bias), one cast to bf16) -- the definition
+    cutlass_scaled_mm implements on the GPU.  The method reads no instance state."""
+    from types import SimpleNamespace
+
+    from vllm.model_executor.kernels.linear.scaled_mm.pytorch import ChannelWiseTorchFP8ScaledMMLinearKernel as K
+
+    g = torch.Generator().manual_seed(777)
+    x = (torch.randn(7, 256, generator=g) * 1.7).to(BF)
+    w = (torch.randn(40, 256, generator=g) * 0.05).to(BF)
+    b = (torch.randn(40, generator=g) * 0.3).to(BF)
+    xq, xs = O.quant_fp8(x, per_token=True)           # bit-pinned to QuantFP8 by fp8_quant_vllm.pt
+    wq, ws = O.quant_fp8(w, per_token=False)
+    out = {"x": x, "w": w, "bias": b, "wq": wq.view(torch.uint8).clone(), "w_scale": ws.clone()}
+    for key, bias in (("y", None), ("y_bias", b)):
+        out[key] = K.apply_scaled_mm(SimpleNamespace(), A=xq, B=wq.t(), out_dtype=BF, As=xs, Bs=ws.reshape(1, 1),
+                                     bias=bias, output_shape=[7, 40]).clone()
+    torch.save(out, OUT / "fp8_linear_vllm.pt")
+    print("wrote fp8_linear_vllm.pt")
 
 
 def tiny_llama_from_hf():
@@ -183,6 +207,7 @@ def tiny_mixtral_from_hf():
 if __name__ == "__main__":
     ops_from_vllm()
     fp8_quant_from_vllm()
+    fp8_linear_from_vllm()
     tiny_llama_from_hf()
     tiny_qwen2_from_hf()
     tiny_mixtral_from_hf()

@@ -146,3 +146,14 @@ def test_moe_topk_ties_go_to_the_lowest_index():
     p = torch.tensor([[0.1, 0.3, 0.3, 0.3], [0.25, 0.25, 0.25, 0.25]])
     v, i = O.moe_topk(p, 2)
     assert i.tolist() == [[1, 2], [0, 1]] and torch.equal(v, torch.tensor([[0.3, 0.3], [0.25, 0.25]]))
+
+
+def test_fp8_linear_against_vllm_torch_fallback():
+    """oracle.fp8_linear == vLLM's ChannelWiseTorchFP8ScaledMMLinearKernel.apply_scaled_mm bit for
+    bit (with and without bias): the restated W8A8 linear is the reference's own definition."""
+    g = torch.load(GOLD / "fp8_linear_vllm.pt", weights_only=False)
+    wq = g["wq"].view(torch.float8_e4m3fn)
+    rq, rs = O.quant_fp8(g["w"], per_token=False)
+    assert torch.equal(rq.view(torch.uint8), g["wq"]) and torch.equal(rs, g["w_scale"])
+    assert torch.equal(O.fp8_linear(g["x"], wq, g["w_scale"]), g["y"])
+    assert torch.equal(O.fp8_linear(g["x"], wq, g["w_scale"], g["bias"]), g["y_bias"])
