@@ -324,3 +324,88 @@ def test_prefix_cache_randomised_content_model():
             assert s.pool._key[b] == d
     assert nreq == 120 and not s.has_work() and s.pool.hits > 0
     assert all(r.finished for r in live.values())
+
+
+# ------------------------------------------------------------------ property test (hypothesis)
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(seed=st.integers(0, 10_000), num_blocks=st.integers(12, 40), max_seqs=st.integers(1, 6),
+       budget=st.sampled_from([16, 48, 64, 200]), caching=st.booleans(), abort_p=st.floats(0.0, 0.2))
+def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budget, caching, abort_p):
+    """Random arrivals / aborts / EOS under KV pressure (forces chunking and preemption): every step
+    respects the token and sequence budgets, chunks continue exactly where the request stopped, block
+    tables of resident rows mirror the requests' block lists, no block is owned twice unless it is a
+    shared (cached, full, read-only) prefix block, and everything is returned at the end."""
+    rng = np.random.RandomState(seed)
+    BS, max_len = 16, 160
+    s = Scheduler(num_blocks, BS, max_seqs, budget, max_len, 2, enable_prefix_caching=caching)
+    heads = [rng.randint(3, 300, size=n).tolist() for n in (16, 40)]
+    live, nreq, steps, finished = {}, 0, 0, 0
+    while steps < 600:
+        steps += 1
+        if nreq < 25 and rng.rand() < 0.4:
+            n_prompt = int(rng.randint(1, 90))
+            head = heads[rng.randint(2)][: rng.randint(0, 41)] if rng.rand() < 0.5 else []
+            prompt = (head + rng.randint(3, 300, size=n_prompt).tolist())[: max_len - 2]
+            max_new = int(rng.randint(1, max(2, min(40, max_len - len(prompt)))))
+            need_blocks = (len(prompt) + max_new + BS) // BS
+            if need_blocks >= num_blocks - 1:
+                continue                                       # the engine rejects these up front
+            r = Request(f"h{nreq}", prompt, SamplingParams(max_tokens=max_new, ignore_eos=bool(rng.rand() < 0.7)))
+            s.add(r); live[r.req_id] = r; nreq += 1
+        if live and rng.rand() < abort_p:
+            rid = list(live)[rng.randint(len(live))]
+            if not live[rid].finished:
+                assert s.abort(rid)
+                assert live[rid].finished and live[rid].finish_reason == "abort" and not live[rid].blocks
+        plan = s.schedule()
+        if plan is None:
+            if nreq >= 25 and not s.has_work():
+                break
+            continue
+        if isinstance(plan, PrefillPlan):
+            assert 0 < plan.num_tokens <= budget and len(plan.reqs) == len(set(id(r) for r in plan.reqs))
+            assert len(s.rows) + len(s.prefilling) <= max_seqs
+            for r, st_, n, smp in zip(plan.reqs, plan.starts, plan.lens, plan.sample):
+                assert n > 0 and st_ == r.num_computed and st_ + n <= r.prefill_target
+                assert smp == (st_ + n == r.prefill_target)
+                assert len(r.blocks) * BS >= r.prefill_target + 1            # room for the first decode slot
+                if caching and st_ > 0 and r in plan.reqs and st_ % BS == 0 and r.num_cached_tokens:
+                    assert r.num_cached_tokens <= r.prefill_target - 1
+            toks = rng.choice([2, 7, 9], size=sum(plan.sample), p=[0.1, 0.45, 0.45]).tolist()
+            out = s.update_prefill(plan, toks)
+        else:
+            B = plan.batch
+            assert 0 < B <= max_seqs and B == len(s.rows)
+            for i, r in enumerate(s.rows):
+                assert r.row == i and int(s.n_blocks[i]) == len(r.blocks)
+                assert s.block_table[i, : len(r.blocks)].tolist() == r.blocks
+                pos = int(s.num_computed[i])
+                assert pos // BS < len(r.blocks) and pos == len(r.prompt_ids) + len(r.output_ids) - 1
+                assert int(s.last_token[i]) == r.all_ids[-1]
+            out = s.update_decode(plan, rng.choice([2, 7, 9], size=B, p=[0.1, 0.45, 0.45]).astype(np.int32))
+        finished += sum(f is not None for f in out.finished)
+        # ownership: a block has several owners only if it is a cached full block inside every owner's computed prefix
+        owners = {}
+        for r in list(s.prefilling) + [x for x in s.rows if x is not None]:
+            assert not r.finished
+            for j, b in enumerate(r.blocks):
+                assert 0 < b < num_blocks
+                owners.setdefault(b, []).append((r, j))
+        for b, lst in owners.items():
+            assert s.pool._ref[b] == len(lst) and b not in s.pool._free
+            if len(lst) > 1:
+                assert caching and s.pool._key[b] is not None
+                assert len({j for _, j in lst}) == 1                        # same logical position in every owner
+        assert len(s.pool._free) + len(owners) == num_blocks - 1
+    assert not s.has_work() or steps >= 600
+    if not s.has_work():
+        assert s.pool.num_free == s.pool.num_total
+        for r in live.values():
+            assert r.finished and (r.finish_reason in ("stop", "length", "abort"))
+            if r.finish_reason == "length":
+                assert len(r.output_ids) == r.params.max_tokens
+            if r.finish_reason == "stop":
+                assert r.output_ids[-1] == 2 and not r.params.ignore_eos
