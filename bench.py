@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--input-len", type=int, default=512)
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--model", default="llama3-8b",
-                    choices=["llama3-8b", "llama3-70b", "tiny", "tiny128", "mixtral-8x7b", "tiny-mixtral"],
+                    choices=["llama3-8b", "llama3-70b", "qwen2-0.5b", "tiny", "tiny128", "mixtral-8x7b", "tiny-mixtral"],
                     help="llama3-8b is the BASELINE config; mixtral-8x7b is a side measurement of the MoE family")
     ap.add_argument("--max-num-batched-tokens", type=int, default=8192, help="prefill token budget per engine step")
     ap.add_argument("--quantization", default=None, choices=[None, "fp8"],
@@ -84,9 +84,10 @@ def host_threads() -> int:
 
 
 def model_config(name):
-    from gpustack_b200.config import llama3_8b, llama3_70b, mixtral_8x7b, tiny_llama, tiny_mixtral
+    from gpustack_b200.config import llama3_8b, llama3_70b, mixtral_8x7b, qwen2_05b, tiny_llama, tiny_mixtral
 
     return {"llama3-8b": llama3_8b, "llama3-70b": llama3_70b, "tiny": tiny_llama, "tiny128": lambda: tiny_llama(128),
+            "qwen2-0.5b": qwen2_05b,
             "mixtral-8x7b": mixtral_8x7b, "tiny-mixtral": tiny_mixtral}[name]()
 
 
@@ -154,7 +155,8 @@ def cpu_reference(mname, n_req, in_len, out_len, state_cpu=None):
 
     from oracle import llama_oracle as O
 
-    cfg = {"llama3-8b": O.LLAMA3_8B, "tiny": O.TINY, "tiny128": O.TINY128}[mname]
+    cfg = {"llama3-8b": O.LLAMA3_8B, "tiny": O.TINY, "tiny128": O.TINY128, "qwen2-0.5b": O.QWEN2_05B_SHAPE,
+           "tiny-mixtral": O.TINY_MIXTRAL}[mname]
     torch.set_num_threads(host_threads())
     if state_cpu is None:
         # values are irrelevant for timing; uniform fill is much faster than randn for 8B params
@@ -167,7 +169,7 @@ def cpu_reference(mname, n_req, in_len, out_len, state_cpu=None):
                     state_cpu[k.replace("layers.0.", f"layers.{l}.")] = v.clone()
         for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
             if k in base:
-                state_cpu[k] = base[k]
+                state_cpu[k] = base[k]                     # tied models (Qwen2-0.5B) have no lm_head entry
     model = O.OracleLlama(cfg, state_cpu, fp32_cache=True)
     prompts = workload(9999, n_req, in_len, cfg.vocab_size)
     ttfts, toks = [], 0

@@ -140,6 +140,15 @@ def llama3_8b() -> ModelConfig:
                        bos_token_id=128000)
 
 
+def qwen2_05b() -> ModelConfig:
+    """BASELINE.json configs[0] model shape (Qwen2-0.5B: q/k/v bias, tied embeddings, GQA group of 7)."""
+    return ModelConfig(vocab_size=151936, hidden_size=896, intermediate_size=4864, num_hidden_layers=24,
+                       num_attention_heads=14, num_key_value_heads=2, head_dim=64, rms_norm_eps=1e-6,
+                       rope_theta=1e6, max_position_embeddings=32768, tie_word_embeddings=True,
+                       attention_bias=True, architecture="Qwen2ForCausalLM", eos_token_id=151643,
+                       bos_token_id=151643)
+
+
 def llama3_70b() -> ModelConfig:
     return ModelConfig(vocab_size=128256, hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
                        num_attention_heads=64, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
