@@ -75,6 +75,7 @@ class _StreamHub:
         self._streams: Dict[str, Tuple[asyncio.AbstractEventLoop, asyncio.Queue]] = {}
         self._stats: Dict[str, RequestStats] = {}
         self._ids = itertools.count()
+        self._forced: Dict[str, str] = {}      # finish reason decided by the HTTP layer (stop strings)
         self.errored: Optional[BaseException] = None
 
     # -- to be provided by the transport
@@ -115,6 +116,11 @@ class _StreamHub:
         for rid, (loop, q) in list(self._streams.items()):
             loop.call_soon_threadsafe(q.put_nowait, ([], "error"))
 
+    def finish_early(self, req_id: str, reason: str) -> None:
+        """The consumer ends the stream itself (e.g. a stop STRING matched): the engine-side request
+        is still aborted when the generator closes, but it is counted with `reason`, not as an abort."""
+        self._forced[req_id] = reason
+
     # -- asyncio side
     def new_request_id(self, prefix: str = "cmpl") -> str:
         return f"{prefix}-{next(self._ids):08x}{int(time.time() * 1000) & 0xffffff:06x}"
@@ -153,9 +159,10 @@ class _StreamHub:
         finally:
             self._streams.pop(req_id, None)
             self._stats.pop(req_id, None)
-            if finished is None:            # client went away
+            forced = self._forced.pop(req_id, None)
+            if finished is None:            # consumer stopped reading: client went away, or a stop string
                 self._abort(req_id)
-                self.metrics.finish(st, "abort")
+                self.metrics.finish(st, forced or "abort")
             else:
                 self.metrics.finish(st, finished)
 
@@ -266,13 +273,14 @@ class EngineCoreServer:
                 if now - last_beat > 1.0:
                     conn.send(("beat", engine_snapshot(eng)))
                     last_beat = now
-        except (EOFError, BrokenPipeError):
+        except (EOFError, OSError):      # the frontend went away (BrokenPipe / ConnectionReset): normal shutdown
             return
         except BaseException as e:  # noqa: BLE001
             try:
                 conn.send(("died", repr(e)))
-            finally:
-                raise
+            except (OSError, ValueError):
+                pass
+            raise
 
 
 class EngineClient(_StreamHub):

@@ -33,10 +33,20 @@ class ModelConfig:
     architecture: str = "LlamaForCausalLM"
     eos_token_id: Optional[int] = None
     bos_token_id: Optional[int] = None
+    eos_token_ids: tuple = ()                # every id that ends a turn (config.json list + generation_config.json)
+    rope_scaling: Optional[dict] = None      # None = plain RoPE; {"rope_type": "llama3" | "linear", ...}
     quantization: Optional[str] = None       # "fp8" when config.json carries an fp8 quantization_config
     num_local_experts: int = 0               # Mixtral: experts per layer (0 = dense MLP)
     sliding_window: Optional[int] = None     # caps max_model_len (full attention == windowed below it)
     num_experts_per_tok: int = 0
+
+    def __post_init__(self):
+        ids = [int(t) for t in self.eos_token_ids]
+        if self.eos_token_id is not None and int(self.eos_token_id) not in ids:
+            ids.insert(0, int(self.eos_token_id))
+        self.eos_token_ids = tuple(ids)
+        if self.eos_token_id is None and ids:
+            self.eos_token_id = ids[0]
 
     @property
     def q_size(self) -> int:
@@ -68,14 +78,26 @@ class ModelConfig:
             raise ValueError(f"unsupported architecture {arch}; supported: {SUPPORTED_ARCHS}")
         heads = d["num_attention_heads"]
         eos = d.get("eos_token_id")
-        if isinstance(eos, list):
-            eos = eos[0] if eos else None
+        eos_all = [int(t) for t in eos] if isinstance(eos, list) else ([] if eos is None else [int(eos)])
+        eos = eos_all[0] if eos_all else None
         rope = d.get("rope_theta")
-        if rope is None and isinstance(d.get("rope_parameters"), dict):
-            rope = d["rope_parameters"].get("rope_theta")
-        scaling = d.get("rope_scaling") or (d.get("rope_parameters") or {}).get("rope_type")
-        if isinstance(scaling, dict) and scaling.get("rope_type", scaling.get("type")) not in (None, "default"):
-            raise ValueError("rope_scaling other than default is not supported yet")
+        rp = d.get("rope_parameters") if isinstance(d.get("rope_parameters"), dict) else None
+        if rope is None and rp is not None:
+            rope = rp.get("rope_theta")
+        # legacy `rope_scaling` dict, or the transformers>=5 `rope_parameters` dict (same keys)
+        sc = d.get("rope_scaling") if isinstance(d.get("rope_scaling"), dict) else rp
+        rope_type = None if sc is None else sc.get("rope_type", sc.get("type"))
+        scaling = None
+        if rope_type not in (None, "default"):
+            if rope_type == "llama3":
+                scaling = {"rope_type": "llama3", "factor": float(sc["factor"]),
+                           "low_freq_factor": float(sc.get("low_freq_factor", 1.0)),
+                           "high_freq_factor": float(sc.get("high_freq_factor", 4.0)),
+                           "original_max_position_embeddings": int(sc["original_max_position_embeddings"])}
+            elif rope_type == "linear":
+                scaling = {"rope_type": "linear", "factor": float(sc["factor"])}
+            else:
+                raise ValueError(f"rope scaling type {rope_type!r} is not supported (supported: default, llama3, linear)")
         quant = None
         qc = d.get("quantization_config")
         if isinstance(qc, dict):
@@ -103,12 +125,50 @@ class ModelConfig:
             max_position_embeddings=d.get("max_position_embeddings", 8192),
             tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
             attention_bias=bool(d.get("attention_bias", arch == "Qwen2ForCausalLM")),
-            architecture=arch, eos_token_id=eos, bos_token_id=d.get("bos_token_id"))
+            architecture=arch, eos_token_id=eos, bos_token_id=d.get("bos_token_id"),
+            eos_token_ids=tuple(eos_all), rope_scaling=scaling)
 
     @staticmethod
     def from_pretrained(model_path: str) -> "ModelConfig":
         with open(Path(model_path) / "config.json") as f:
-            return ModelConfig.from_dict(json.load(f))
+            cfg = ModelConfig.from_dict(json.load(f))
+        # chat checkpoints list their turn terminators (<|eot_id|>, ...) in generation_config.json
+        gen = Path(model_path) / "generation_config.json"
+        if gen.exists():
+            try:
+                e = json.loads(gen.read_text()).get("eos_token_id")
+            except (OSError, ValueError):
+                e = None
+            extra = [int(t) for t in e] if isinstance(e, list) else ([] if e is None else [int(e)])
+            cfg.eos_token_ids = tuple(dict.fromkeys(list(cfg.eos_token_ids) + extra))
+            if cfg.eos_token_id is None and cfg.eos_token_ids:
+                cfg.eos_token_id = cfg.eos_token_ids[0]
+        return cfg
+
+    def rope_inv_freq(self):
+        """Inverse RoPE frequencies [head_dim/2] (fp32 torch tensor), with the checkpoint's frequency
+        scaling applied ($VLLM/model_executor/layers/rotary_embedding/llama3_rope.py,
+        linear_scaling_rope.py; same arithmetic as transformers' ROPE_INIT_FUNCTIONS)."""
+        import math
+
+        import torch
+
+        D = self.head_dim
+        inv = 1.0 / (self.rope_theta ** (torch.arange(0, D, 2, dtype=torch.float) / D))
+        sc = self.rope_scaling
+        if not sc:
+            return inv
+        if sc["rope_type"] == "linear":
+            return inv / sc["factor"]
+        factor, lo, hi = sc["factor"], sc["low_freq_factor"], sc["high_freq_factor"]
+        old = sc["original_max_position_embeddings"]
+        low_wl, high_wl = old / lo, old / hi
+        wl = 2 * math.pi / inv
+        scaled = torch.where(wl > low_wl, inv / factor, inv)
+        smooth = (old / wl - lo) / (hi - lo)
+        mid = (1 - smooth) * inv / factor + smooth * inv
+        is_mid = (wl >= high_wl) & (wl <= low_wl)
+        return torch.where(is_mid, mid, scaled)
 
     def to_hf_dict(self) -> dict:
         extra = {"quantization_config": {"quant_method": "fp8", "activation_scheme": "dynamic"}} \
@@ -128,7 +188,9 @@ class ModelConfig:
             "max_position_embeddings": self.max_position_embeddings,
             "tie_word_embeddings": self.tie_word_embeddings, "attention_bias": self.attention_bias,
             "hidden_act": "silu", "torch_dtype": "bfloat16", "bos_token_id": self.bos_token_id or 1,
-            "eos_token_id": self.eos_token_id if self.eos_token_id is not None else 2,
+            "eos_token_id": (list(self.eos_token_ids) if len(self.eos_token_ids) > 1 else
+                             (self.eos_token_id if self.eos_token_id is not None else 2)),
+            **({"rope_scaling": dict(self.rope_scaling)} if self.rope_scaling else {}),
         }
 
 

@@ -25,7 +25,7 @@ from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, ra
 
 log = logging.getLogger("b200.engine")
 
-_KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED = 0, 1, 2, 3, 4
+_KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED, _KIND_GATHER = 0, 1, 2, 3, 4, 5
 
 
 class ShmStepChannel:
@@ -187,7 +187,7 @@ class LLMEngine:
         self.runner.init_kv_cache(n)
         self.runner.capture_graphs()
         self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
-                               ecfg.max_model_len, mcfg.eos_token_id, ecfg.enable_prefix_caching)
+                               ecfg.max_model_len, mcfg.eos_token_ids or mcfg.eos_token_id, ecfg.enable_prefix_caching)
         self.requests: Dict[str, Request] = {}
         self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
         self.step_time = {"prefill": 0.0, "decode": 0.0}
@@ -286,8 +286,10 @@ class LLMEngine:
     def _apply_sampling(self, reqs, toks):
         """Override the in-graph greedy tokens of requests that asked for temperature > 0."""
         rows = [i for i, r in enumerate(reqs) if r.params.temperature > 0.0]
-        if not rows or self.tp is not None:      # TP>1: vocab-sharded logits -> greedy (documented)
+        if not rows:
             return toks
+        if self.tp is not None:      # every rank joins the all-gather of the vocab-sharded logits rows
+            self.tp.bcast_step([_KIND_GATHER, len(rows)], np.asarray(rows, dtype=np.int32))
         gens = []
         for i in rows:
             r = reqs[i]
@@ -381,6 +383,9 @@ class TPWorker:
                 continue
             if kind == _KIND_MAXELAPSED:
                 self.engine._do_max_elapsed()
+                continue
+            if kind == _KIND_GATHER:
+                run.gather_logits_rows(p[:h[1]].tolist())     # rank 0 samples; this rank only contributes
                 continue
             if kind == _KIND_DECODE:
                 B = h[1]

@@ -118,8 +118,7 @@ class ModelRunner:
 
     def _cos_sin_cache(self) -> torch.Tensor:
         # $VLLM/model_executor/layers/rotary_embedding/base.py:71-93; kept in the model dtype
-        D = self.D
-        inv_freq = 1.0 / (self.mcfg.rope_theta ** (torch.arange(0, D, 2, dtype=torch.float) / D))
+        inv_freq = self.mcfg.rope_inv_freq()    # plain, llama3- or linearly-scaled frequencies
         t = torch.arange(self.max_model_len, dtype=torch.float)
         freqs = torch.einsum("i,j -> ij", t, inv_freq)
         return torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(BF16)
@@ -446,15 +445,30 @@ class ModelRunner:
         return self.out_host[:ns].numpy().copy()
 
     # ------------------------------------------------------------------------------ sampling
+    def gather_logits_rows(self, rows: Sequence[int]) -> torch.Tensor:
+        """Full-vocabulary fp32 logits [len(rows), V] of the given rows of the last step.  TP>1: the
+        vocab shards are all-gathered over NCCL (every rank must call this with the same rows; the
+        reference engine gathers logits the same way, $VLLM/model_executor/layers/logits_processor.py)."""
+        idx = torch.tensor(list(rows), dtype=torch.long, device=self.device)
+        local = self.logits.index_select(0, idx)
+        if self.tp == 1:
+            return local
+        V = self.mcfg.vocab_size
+        per = (V + self.tp - 1) // self.tp
+        if local.shape[1] < per:                     # last rank of an uneven split
+            local = torch.nn.functional.pad(local, (0, per - local.shape[1]), value=float("-inf"))
+        out = torch.empty(self.tp, len(rows), per, dtype=torch.float32, device=self.device)
+        torch.distributed.all_gather_into_tensor(out, local.contiguous(), group=self.tp_group)
+        return out.permute(1, 0, 2).reshape(len(rows), self.tp * per)[:, :V]
+
     def sample_rows(self, rows: Sequence[int], temps: Sequence[float], top_ps: Sequence[float],
                     generators: Sequence[Optional[torch.Generator]]) -> List[int]:
         """Temperature / nucleus sampling for the given rows of the last step's logits (the greedy
         path stays inside the captured graph; sampled rows are overridden afterwards, as
-        $VLLM/v1/sample/sampler.py does with its greedy/random split).  TP>1: logits are
-        vocab-sharded, callers fall back to greedy."""
-        idx = torch.tensor(list(rows), dtype=torch.long, device=self.device)
-        lg = self.logits.index_select(0, idx) / torch.tensor(list(temps), dtype=torch.float32,
-                                                              device=self.device).clamp_min(1e-5).unsqueeze(1)
+        $VLLM/v1/sample/sampler.py does with its greedy/random split).  TP>1: rank 0 samples from the
+        gathered full-vocabulary logits (the other ranks only take part in the gather)."""
+        lg = self.gather_logits_rows(rows) / torch.tensor(list(temps), dtype=torch.float32,
+                                                          device=self.device).clamp_min(1e-5).unsqueeze(1)
         probs = torch.softmax(lg, dim=-1)
         tp = torch.tensor(list(top_ps), dtype=torch.float32, device=self.device).unsqueeze(1)
         if bool((tp < 1.0).any()):

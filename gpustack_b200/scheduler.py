@@ -84,13 +84,22 @@ class StepOutput:
 
 class Scheduler:
     def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: int, eos_token_id: Optional[int], enable_prefix_caching: bool = False):
+                 max_model_len: int, eos_token_id, enable_prefix_caching: bool = False):
+        """eos_token_id: one id, an iterable of ids (every turn terminator of the checkpoint), or None."""
         self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching)
         self.block_size = block_size
         self.max_num_seqs = max_num_seqs
         self.max_tokens_per_step = max_num_batched_tokens
         self.max_model_len = max_model_len
-        self.eos = -1 if eos_token_id is None else int(eos_token_id)
+        if eos_token_id is None:
+            eos_ids = []
+        elif isinstance(eos_token_id, (int, np.integer)):
+            eos_ids = [int(eos_token_id)]
+        else:
+            eos_ids = [int(t) for t in eos_token_id]
+        self.eos_ids = frozenset(eos_ids)
+        self.eos = eos_ids[0] if eos_ids else -1
+        self._eos_arr = np.asarray(sorted(self.eos_ids), dtype=np.int32)
         self.max_blocks_per_seq = (max_model_len + block_size - 1) // block_size
         self.waiting: Deque[Request] = deque()
         self.prefilling: List[Request] = []     # admitted, prompt not fully computed yet
@@ -283,7 +292,9 @@ class Scheduler:
     # ------------------------------------------------------------------ results
     def _finish_reason(self, r: Request, tok: int) -> Optional[str]:
         p = r.params
-        if not p.ignore_eos and (tok == self.eos or tok in p.stop_token_ids):
+        # ignore_eos suppresses only EOS; stop_token_ids always terminate (reference engine semantics,
+        # $VLLM/v1/core/sched/utils.py check_stop)
+        if (not p.ignore_eos and tok in self.eos_ids) or tok in p.stop_token_ids:
             return "stop"
         if len(r.output_ids) >= p.max_tokens:
             return "length"
@@ -320,7 +331,10 @@ class Scheduler:
         self.num_computed[:B] += 1
         self.remaining[:B] -= 1
         done = self.remaining[:B] <= 0
-        stop = self.check_eos[:B] & (sampled == self.eos)
+        if len(self._eos_arr) == 1:
+            stop = self.check_eos[:B] & (sampled == self.eos)
+        else:
+            stop = self.check_eos[:B] & np.isin(sampled, self._eos_arr)
         out = StepOutput([], sampled.tolist(), [None] * B)
         rows = list(self.rows)
         out.req_ids = [r.req_id for r in rows]
@@ -331,7 +345,7 @@ class Scheduler:
         # per-request stop_token_ids are rare; only requests that set them pay for the check
         for i, r in enumerate(rows):
             p = r.params
-            if p.stop_token_ids and not p.ignore_eos and toks[i] in p.stop_token_ids:
+            if p.stop_token_ids and toks[i] in p.stop_token_ids:
                 fin[i] = True
                 stop[i] = True
         for i in np.nonzero(fin)[0][::-1].tolist():   # descending: swaps never touch pending rows

@@ -159,6 +159,7 @@ def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_l
                         pending += delta
                         cut = min((pending.find(s) for s in stops if s in pending), default=-1)
                         if cut >= 0:
+                            aeng.finish_early(rid, "stop")      # counted as a stop, not as an abort
                             yield pending[:cut], "stop", first, n_out
                             return
                         if fin is None and hold > 0:

@@ -7,6 +7,8 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+if str(ROOT / "tests") not in sys.path:      # test-only helpers (gpustack_compat.py, tp_parity_main.py)
+    sys.path.insert(0, str(ROOT / "tests"))
 
 
 def pytest_configure(config):

@@ -7,7 +7,7 @@ from pathlib import Path
 import pytest
 import yaml
 
-from gpustack_b200 import gpustack_compat as gc
+import gpustack_compat as gc   # tests/gpustack_compat.py (test infrastructure)
 from gpustack_b200.cli import build_parser
 
 ROOT = Path(__file__).resolve().parents[1]

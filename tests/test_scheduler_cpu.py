@@ -80,6 +80,24 @@ def test_eos_and_stop_ids_finish_with_stop():
     assert [r.req_id for r in s.rows] == ["r2"]
 
 
+def test_ignore_eos_suppresses_only_eos_and_every_eos_id_counts():
+    """Reference-engine semantics: ignore_eos never disables stop_token_ids; a checkpoint may list
+    several turn terminators (config.json list + generation_config.json)."""
+    s = Scheduler(64, 16, 8, 64, 256, (2, 5))
+    s.add(req(0, 5, max_tokens=10, ignore_eos=True, stop_token_ids=(9,)))
+    s.add(req(1, 5, max_tokens=10))
+    s.add(req(2, 5, max_tokens=10, ignore_eos=True))
+    drive(s, s.schedule(), tok=7)
+    out = s.update_decode(s.schedule(), np.array([9, 5, 5], dtype=np.int32))
+    assert out.finished == ["stop", "stop", None]
+    # the same rules on the prefill path (first sampled token)
+    s2 = Scheduler(64, 16, 8, 64, 256, (2, 5))
+    s2.add(req(0, 5, max_tokens=10, ignore_eos=True, stop_token_ids=(9,)))
+    s2.add(req(1, 5, max_tokens=10))
+    out = s2.update_prefill(s2.schedule(), [9, 5])
+    assert out.finished == ["stop", "stop"]
+
+
 def test_preemption_recomputes_and_never_loses_tokens():
     s = mk(num_blocks=8, max_seqs=4, budget=64, max_len=128)   # 7 usable blocks = 112 token slots
     for i in range(3):

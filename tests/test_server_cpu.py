@@ -127,6 +127,21 @@ def test_stop_string_truncates_and_reports_stop(client):
     assert j["choices"][0]["text"] == "Hello from the " and j["choices"][0]["finish_reason"] == "stop"
 
 
+def test_stop_string_is_counted_as_stop_not_abort(client):
+    def counts():
+        out = {}
+        for line in client.get("/metrics").text.splitlines():
+            if line.startswith("vllm:request_success_total"):
+                out[line.split('finished_reason="')[1].split('"')[0]] = float(line.rsplit(" ", 1)[1])
+        return out
+
+    before = counts()
+    client.post("/v1/completions", json={"model": "stub-model", "prompt": "abc", "max_tokens": 60,
+                                         "ignore_eos": True, "stop": ["stub"]})
+    after = counts()
+    assert after["stop"] == before["stop"] + 1 and after["abort"] == before["abort"]
+
+
 def test_error_envelopes(client):
     r = client.post("/v1/chat/completions", json={"model": "other", "messages": [{"role": "user", "content": "x"}]})
     assert r.status_code == 404 and r.json()["error"]["code"] == "model_not_found"

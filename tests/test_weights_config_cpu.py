@@ -101,8 +101,10 @@ def test_config_parsing_and_byte_accounting():
     assert m.head_dim == 16 and m.num_key_value_heads == 4 and m.eos_token_id == 7
     with pytest.raises(ValueError):
         ModelConfig.from_dict({**hf, "architectures": ["DeepseekV3ForCausalLM"]})
-    with pytest.raises(ValueError):
-        ModelConfig.from_dict({**hf, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+    with pytest.raises(ValueError):   # yarn / dynamic scaling change attention scaling too: refused, never ignored
+        ModelConfig.from_dict({**hf, "rope_scaling": {"rope_type": "yarn", "factor": 8.0}})
+    with pytest.raises(ValueError):   # the transformers>=5 spelling must not slip through either
+        ModelConfig.from_dict({**hf, "rope_parameters": {"rope_type": "yarn", "factor": 8.0, "rope_theta": 1e4}})
     e = EngineConfig(max_num_seqs=100)
     b = e.graph_buckets()
     assert b[0] == 1 and b[-1] == 100 and b == sorted(set(b))
@@ -343,3 +345,44 @@ def test_lazy_random_source_is_deterministic_and_complete():
         if cfg.num_local_experts:
             assert w.layers[0].w13.shape[0] == cfg.num_local_experts * 2 * cfg.intermediate_size
             assert float(w.layers[0].router[:8].float().std()) > 5 * float(w.layers[0].w2.float().std())
+
+
+def test_rope_scaling_matches_transformers_and_eos_ids_are_all_kept(tmp_path):
+    """Llama-3.1-style and linear RoPE scaling (legacy `rope_scaling` and the transformers>=5
+    `rope_parameters` spelling) give the inverse frequencies transformers computes; every EOS id of
+    config.json + generation_config.json ends a turn."""
+    import json
+
+    import torch
+    from transformers import LlamaConfig
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+
+    hf = tiny_llama(128).to_hf_dict()
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+    for spelling in ("rope_scaling", "rope_parameters"):
+        d = {**hf, "max_position_embeddings": 131072, "rope_theta": 500000.0}
+        d[spelling] = {**l3, "rope_theta": 500000.0} if spelling == "rope_parameters" else l3
+        m = ModelConfig.from_dict(d)
+        assert m.rope_scaling["rope_type"] == "llama3"
+        ours = m.rope_inv_freq()
+        ref_cfg = LlamaConfig(hidden_size=m.hidden_size, num_attention_heads=m.num_attention_heads, head_dim=m.head_dim,
+                              max_position_embeddings=131072, rope_theta=500000.0,
+                              rope_scaling={**l3, "rope_theta": 500000.0})
+        ref, _ = ROPE_INIT_FUNCTIONS["llama3"](ref_cfg, "cpu")
+        torch.testing.assert_close(ours, ref.float(), rtol=1e-6, atol=0)
+        assert not torch.equal(ours, ModelConfig.from_dict(hf).rope_inv_freq() * 0 + ours[0])  # really scaled
+    lin = ModelConfig.from_dict({**hf, "rope_scaling": {"type": "linear", "factor": 4.0}})
+    base = ModelConfig.from_dict(hf)
+    torch.testing.assert_close(lin.rope_inv_freq(), base.rope_inv_freq() / 4.0)
+    assert ModelConfig.from_dict({**hf, "rope_scaling": {"rope_type": "default"}}).rope_scaling is None
+    # round trip through to_hf_dict keeps the scaling
+    assert ModelConfig.from_dict(lin.to_hf_dict()).rope_scaling == lin.rope_scaling
+
+    # EOS ids: list in config.json, more in generation_config.json
+    d = tmp_path / "m"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps({**hf, "eos_token_id": [7, 9]}))
+    (d / "generation_config.json").write_text(json.dumps({"eos_token_id": [7, 11]}))
+    m = ModelConfig.from_pretrained(str(d))
+    assert m.eos_token_id == 7 and m.eos_token_ids == (7, 9, 11)
