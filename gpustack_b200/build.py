@@ -52,14 +52,15 @@ def _digest(paths) -> str:
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> Path:
-    """variant "" = the product library; "late" = libb200_late.so, the experimental build whose kernels
-    release their programmatic dependents only after their own dependency wait (-DB200_PDL_LATE_TRIGGER)."""
+    """variant "" = the product library (dependents released after the kernel's own dependency wait);
+    "early" = libb200_early.so, the experimental build with the round-1 entry-time trigger
+    (-DB200_PDL_EARLY_TRIGGER), kept only to reproduce the hazard documented in DESIGN.md section 9."""
     srcs = [CSRC / s for s in SOURCES]
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [
         CSRC.parent.parent / "include" / "b200.h"
     ]
     lib = LIB if not variant else CSRC / f"libb200_{variant}.so"
-    extra = {"": [], "late": ["-DB200_PDL_LATE_TRIGGER=1"]}[variant]
+    extra = {"": [], "early": ["-DB200_PDL_EARLY_TRIGGER=1"]}[variant]
     objdir = CSRC / ("build" if not variant else f"build_{variant}")
     stamp = objdir / "stamp"
     digest = _digest(deps) + variant
@@ -91,4 +92,4 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> Path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, variant="late" if "--late" in sys.argv else ""))
+    print(build(force="--force" in sys.argv, verbose=True, variant="early" if "--early" in sys.argv else ""))

@@ -58,7 +58,27 @@ __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
-// 16-byte streaming global loads/stores (read-once data: skip L1 allocation)
+// 16-byte loads of buffers a PRECEDING kernel of the same step wrote (activations, split-K partials,
+// logits): served from L2, never from this SM's L1, so they stay coherent even when grids of a
+// programmatic-dependent-launch chain overlap (ld.global.nc / __ldg are reserved for data that is
+// constant for the whole step: weights, cos/sin tables, index buffers).
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const void* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+// 16-byte streaming global loads/stores (read-once, step-constant data: skip L1 allocation)
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -91,22 +111,26 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------- programmatic dependent launch (PDL)
-// Every kernel starts with pdl_launch_dependents() (the next kernel in the stream may be scheduled
-// and run its prologue while this one is still executing) and calls pdl_wait() before its first
-// global-memory access (blocks until the preceding kernel has completed and flushed).
-#ifdef B200_PDL_LATE_TRIGGER
-// Experimental variant (libb200_late.so, tools/debug_moe_graph.py): dependents are released only
-// AFTER this kernel's own dependency wait, so at most two kernels of a chain are resident at once.
+// Every kernel calls pdl_launch_dependents() at entry and pdl_wait() before its first global-memory
+// access (blocks until the preceding kernel has completed and flushed); everything in between
+// (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.
+// Dependents are released only AFTER this kernel's own dependency wait: at most two grids of a chain
+// are resident at once, and a grid can only become resident after its predecessor's predecessor
+// has completed.  (Releasing at entry lets dozens of small grids of a decode step pile up; a CTA of a
+// later grid that was made resident early does not see the launch-time L1 invalidation it relies on,
+// and CUDA-graph replays of the MoE decode step computed wrong logits that way -- DESIGN.md
+// section 9.  -DB200_PDL_EARLY_TRIGGER rebuilds the old behaviour for experiments.)
+#ifdef B200_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
 __device__ __forceinline__ void pdl_launch_dependents() {}
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-#else
-__device__ __forceinline__ void pdl_launch_dependents() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
 // ------------------------------------------------------------------ clusters
@@ -157,6 +181,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Bounded wait: a protocol bug becomes a trapped kernel (reported as a CUDA error) instead of a hung
+// GPU.  globaltimer is only consulted every 4096 failed probes.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -183,6 +222,26 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1),
         "l"(cache_hint)
       : "memory");
+}
+// 3-D tiled STORE shared -> global (bulk async group): coordinates (inner element, row, plane);
+// parts of the box outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// at most N of this thread's bulk groups may still be in flight (writes not yet performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 // L2 eviction-priority hints (same encodings CUTLASS passes as TMA::CacheHintSm90)
 static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -339,6 +398,37 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// registers -> 32 lanes x 32 columns of TMEM (thread t writes lane base_lane + t)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 
 // K-major, 128B-swizzled shared-memory operand descriptor (rows are 128 bytes,
 // 8-row groups are 1024 bytes apart).  Bit layout follows the sm_100 matrix
@@ -353,9 +443,27 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;             // SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled operand (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units:
+// one K index = one 128-byte row of 64 contiguous MN elements, 8 such rows = one 1024-byte swizzle
+// atom, the next 8 K rows are SBO bytes further, the next 64 MN elements LBO bytes further).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// same with the B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t n) {
+  return umma_idesc_bf16(m, n) | (1u << 16);
 }
 
 // kind::f8f6f4 instruction descriptor: e4m3 x e4m3 -> fp32 (a/b format 0), both operands K-major.

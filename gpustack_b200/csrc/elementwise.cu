@@ -22,8 +22,8 @@ silu_and_mul_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, i
     const size_t t = idx / vec_per_row;
     const int vi = (int)(idx % vec_per_row);
     const bf16* g = x + t * (size_t)(2 * I) + (size_t)vi * 8;
-    const uint4 ga = ld_nc_v4(g);
-    const uint4 ua = ld_nc_v4(g + I);
+    const uint4 ga = ld_cg_v4(g);
+    const uint4 ua = ld_cg_v4(g + I);
     const uint32_t gw[4] = {ga.x, ga.y, ga.z, ga.w};
     const uint32_t uw[4] = {ua.x, ua.y, ua.z, ua.w};
     uint32_t ow[4];
@@ -91,7 +91,7 @@ splitk_reduce_kernel(const float* __restrict__ P, int S, bf16* __restrict__ Y, i
     const int vi = (int)(idx % vec_per_row);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < S; ++s) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(P + s * plane + m * N) + vi);
+      const float4 p = ld_cg_f4(reinterpret_cast<const float4*>(P + s * plane + m * N) + vi);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
     uint2 o;
@@ -115,7 +115,7 @@ argmax_f32_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __restr
   int best_i = 0x7fffffff;
   const int nvec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
   for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + vi);
+    const float4 v = ld_cg_f4(reinterpret_cast<const float4*>(row) + vi);
     const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

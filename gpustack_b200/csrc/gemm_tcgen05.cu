@@ -6,8 +6,10 @@
 //     memory stages guarded by full/empty mbarriers;
 //   * one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator
 //     in tensor memory, double-buffered so the epilogue of tile i overlaps the main loop of i+1;
-//   * four epilogue warps read the accumulator back with tcgen05.ld and store bf16 (or fp32
-//     split-K partials) straight to global memory;
+//   * four epilogue warps read the accumulator back with tcgen05.ld (one weight row per thread),
+//     transpose 32 x 32 blocks through shared memory and hand them to TMA STORES
+//     (cp.async.bulk.tensor, clipped by the hardware at the M / N edges) -- bf16, fp32 logits or
+//     fp32 split-K partial planes;
 //   * the kernel is persistent: grid = #SMs, tiles are walked with a grouped raster so that a
 //     wave shares activation tiles through L2.
 //
@@ -28,33 +30,25 @@ constexpr int kBlockW = 128;  // weight rows per tile  (UMMA M)
 constexpr int kBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 192;  // warp0 TMA, warp1 MMA+TMEM alloc, warps 2-5 epilogue
+// epilogue staging: every epilogue warp owns two 4 KB buffers (a 32 x 32 block of fp32, or of bf16
+// in the first half) that alternate between "being filled" and "being read by a TMA store"
+constexpr int kStgBufBytes = 4096;
+constexpr int kStgWarpBytes = 2 * kStgBufBytes;
+constexpr int kStgBytes = 4 * kStgWarpBytes;
+constexpr int kRingBudget = 192 * 1024;  // operand ring; + staging + barriers + alignment <= 227 KB
+constexpr int kBarBytes = 256;
 
 template <int BLOCK_X>
 struct GemmCfg {
   static constexpr int kABytes = kBlockW * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_X * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // as many stages as fit in ~200 KB: deep rings keep >100 KB of weight loads in flight per SM,
+  // as many stages as fit in 192 KB: deep rings keep >100 KB of weight loads in flight per SM,
   // which is what an HBM-bound decode tile needs (latency x per-SM share of 6.5 TB/s).
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 12 ? 12 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kRingBudget / kStageBytes > 12 ? 12 : kRingBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_X < 32 ? 32 : 2 * BLOCK_X;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 /*align*/ + kBarBytes;
 };
-
-__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
-  // Bounded wait: a protocol bug becomes a trapped kernel (reported as a CUDA error) instead of
-  // a hung GPU.  globaltimer is only consulted every 4096 failed probes.
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 4095u) == 0) {
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  }
-}
 
 struct TileCoord {
   int split, m_tile, n_tile;
@@ -77,18 +71,23 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
   return c;
 }
 
-// TMEM accumulator (this warp's 32 lanes x BLOCK_X columns) -> global memory.
+// TMEM accumulator (this warp's 32 lanes = 32 weight rows x BLOCK_X token columns) -> global memory.
+// A thread owns ONE output column n and BLOCK_X rows m of Y[m, n]: written directly that would be
+// one 2-byte store per element at stride ldy.  Instead each 32-column chunk is transposed through
+// this warp's staging buffer ([m][n] rows of 64 / 128 / 32 bytes, conflict-free: the 32 lanes of a
+// store instruction fill one row) and leaves as ONE TMA store per chunk; the hardware clips rows
+// >= M and columns >= N, so tail tiles need no predicates.  Two buffers alternate so that chunk i+1
+// is filled while the store of chunk i still reads its buffer.
 // EPI 0: bf16 / fp32 store; EPI 1: SiLU*mul of interleaved gate/up rows (see the kernel comment).
 // FP8 1: W8A8 dequantisation -- every accumulator is multiplied by the token's dynamic activation
 //        scale xs[m] and the weight row's scale ws (already loaded by the caller) before any
 //        rounding, as cutlass_scaled_mm does in the reference engine.
+// n0: first output column (weight row) of this warp; `which` (in/out): staging buffer to fill next.
 template <int BLOCK_X, int EPI, int FP8 = 0>
-__device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, size_t split_off, int n,
-                                                    int m_base, int M, int N, int64_t ldy, int out_f32,
-                                                    int lane, const float* __restrict__ xs = nullptr,
-                                                    float ws = 1.f) {
-  bf16* Yb = reinterpret_cast<bf16*>(Yv);
-  float* Yf = reinterpret_cast<float*>(Yv);
+__device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, const CUtensorMap* tmap_y, uint8_t* stg,
+                                                    int& which, int n0, int m_base, int split, int M, int N,
+                                                    int out_f32, int lane,
+                                                    const float* __restrict__ xs = nullptr, float ws = 1.f) {
   constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
 #pragma unroll 1
   for (int c0 = 0; c0 < BLOCK_X; c0 += CH) {
@@ -101,16 +100,21 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, s
       const int m = m_base + c0 + lane;   // lane j holds the scale of column j of this chunk
       xs_lane = (lane < CH && m < M) ? xs[m] : 0.f;
     }
+    // the store that read this buffer two chunks ago must have drained it before it is refilled
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
     tmem_ld_wait();
     if constexpr (FP8) {
 #pragma unroll
       for (int j = 0; j < CH; ++j)
         r[j] = __float_as_uint(__uint_as_float(r[j]) * (__shfl_sync(0xffffffffu, xs_lane, j) * ws));
     }
+    uint8_t* buf = stg + which * kStgBufBytes;
+    const uint32_t sbuf = smem_u32(buf);
     if constexpr (EPI == 1) {
-      const int ch = n >> 1;          // output channel of this lane pair
-      bf16* dst = Yb + (size_t)(m_base + c0) * ldy + ch;
+      // lane pair (2p, 2p+1) = (gate, up) rows of output channel n0/2 + p; staging rows are 16 channels
       const bool odd = lane & 1;
+      const uint32_t col = sbuf + (uint32_t)(lane >> 1) * 2u;
 #pragma unroll
       for (int j = 0; j < CH; j += 2) {
         // even lane (gate row) computes token j, odd lane (up row) computes token j+1
@@ -119,22 +123,28 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, s
         const float g = round_bf16(__uint_as_float(odd ? recv : r[j]));
         const float up = round_bf16(__uint_as_float(odd ? r[j + 1] : recv));
         const float sg = round_bf16(g / (1.f + __expf(-g)));
-        const int m = m_base + c0 + j + (odd ? 1 : 0);
-        if (n < N && m < M) dst[(size_t)(j + (odd ? 1 : 0)) * ldy] = __float2bfloat16_rn(sg * up);
+        const bf16 v = __float2bfloat16_rn(sg * up);
+        st_shared_u16(col + (uint32_t)(j + (odd ? 1 : 0)) * 32u, *reinterpret_cast<const uint16_t*>(&v));
       }
-    } else if (n < N) {
-      if (out_f32) {
-        float* dst = Yf + split_off + (size_t)(m_base + c0) * ldy + n;
+    } else if (out_f32) {
+      const uint32_t col = sbuf + (uint32_t)lane * 4u;
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __uint_as_float(r[j]);
-      } else {
-        bf16* dst = Yb + (size_t)(m_base + c0) * ldy + n;
+      for (int j = 0; j < CH; ++j) st_shared_u32(col + (uint32_t)j * 128u, r[j]);
+    } else {
+      const uint32_t col = sbuf + (uint32_t)lane * 2u;
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (m_base + c0 + j < M) dst[(size_t)j * ldy] = __float2bfloat16_rn(__uint_as_float(r[j]));
+      for (int j = 0; j < CH; ++j) {
+        const bf16 v = __float2bfloat16_rn(__uint_as_float(r[j]));
+        st_shared_u16(col + (uint32_t)j * 64u, *reinterpret_cast<const uint16_t*>(&v));
       }
     }
+    fence_proxy_async();   // generic-proxy writes above -> visible to the TMA (async proxy) read below
+    __syncwarp();
+    if (lane == 0 && n0 < N) {
+      tma_store_3d(tmap_y, buf, EPI == 1 ? (n0 >> 1) : n0, m_base + c0, split);
+      bulk_commit();
+    }
+    which ^= 1;
   }
 }
 
@@ -152,15 +162,16 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, void* Yv, s
 template <int BLOCK_X, int EPI, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                         const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
-                         int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
-                         int m_tiles, int group_m) {
+                         const __grid_constant__ CUtensorMap tmap_x,
+                         const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
+                         int splits, int n_tiles, int m_tiles, int group_m) {
   using Cfg = GemmCfg<BLOCK_X>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* stg_base = smem + STAGES * Cfg::kStageBytes;   // epilogue staging (1024-byte aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + kStgBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -174,6 +185,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], MC);  // one multicast commit per CTA of the cluster
@@ -267,22 +279,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    uint8_t* stg = stg_base + quad * kStgWarpBytes;
+    int which = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = first_unit; u < total_units; u += unit_stride) {
       const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
       mbar_wait_guarded(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int n = (c.n_tile * MC + (int)crank) * kBlockW + quad * 32 + lane;
+      const int n0 = (c.n_tile * MC + (int)crank) * kBlockW + quad * 32;
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
-      const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
-      epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
+      epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();   // every TMA store of this warp has been performed
   }
 
   tc_fence_before();
@@ -309,9 +323,9 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kBlockW * kBlockK * 2;
   static constexpr int kBBytes = kHalf * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 10 ? 10 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kRingBudget / kStageBytes > 10 ? 10 : kRingBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_X < 32 ? 32 : 2 * BLOCK_X;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 + kBarBytes;
 };
 
 // FP8 1: e4m3 x e4m3 -> fp32 (kind::f8f6f4).  A k-block is still one 128-byte swizzle row, i.e.
@@ -331,7 +345,7 @@ struct GroupInfo {
 
 template <int BLOCK_X, int EPI, int FP8, int GROUPED = 0>
 __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const CUtensorMap& tmap_x,
-                                              void* __restrict__ Yv, int M, int N, int K, int64_t ldy,
+                                              const CUtensorMap& tmap_y, int M, int N, int K,
                                               int out_f32, int splits, int n_tiles, int m_tiles,
                                               int group_m, const float* __restrict__ xscale,
                                               const float* __restrict__ wscale, int wscale_stride,
@@ -342,7 +356,8 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* stg_base = smem + STAGES * Cfg::kStageBytes;   // epilogue staging (1024-byte aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + kStgBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -357,6 +372,7 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 2);   // (leader's copy is the live one) one expect_tx arrive per CTA
       mbar_init(&empty_bar[i], 1);  // one multicast commit from the leader
@@ -449,31 +465,34 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
+    uint8_t* stg = stg_base + quad * kStgWarpBytes;
+    int which = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = first_unit; u < total_units; u += unit_stride) {
       const TileCoord c = decode_unit(u, n_units, m_tiles, splits, group_m);
       mbar_wait_guarded(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int n = (c.n_tile * 2 + (int)crank) * kBlockW + quad * 32 + lane;
+      const int n0 = (c.n_tile * 2 + (int)crank) * kBlockW + quad * 32;
+      const int n = n0 + lane;
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
-      const size_t split_off = (size_t)c.split * (size_t)M * (size_t)ldy;
       if constexpr (FP8) {
         const float ws = n < N ? wscale[(size_t)n * wscale_stride] : 0.f;
-        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane,
+        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane,
                                              xscale, ws);
       } else if (GROUPED && xscale != nullptr) {
-        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane,
+        epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane,
                                              xscale, 1.f);
       } else {
-        epilogue_store_tile<BLOCK_X, EPI>(t_addr, Yv, split_off, n, m_base, M, N, ldy, out_f32, lane);
+        epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();   // every TMA store of this warp has been performed
   }
 
   tc_fence_before();
@@ -488,10 +507,10 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
 template <int BLOCK_X, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
-                             int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
-                             int m_tiles, int group_m) {
-  gemm_2sm_body<BLOCK_X, EPI, 0>(tmap_w, tmap_x, Yv, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
+                             const __grid_constant__ CUtensorMap tmap_x,
+                             const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
+                             int splits, int n_tiles, int m_tiles, int group_m) {
+  gemm_2sm_body<BLOCK_X, EPI, 0>(tmap_w, tmap_x, tmap_y, M, N, K, out_f32, splits, n_tiles, m_tiles,
                                  group_m, nullptr, nullptr, 0);
 }
 
@@ -502,11 +521,12 @@ gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
 template <int BLOCK_X, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_fp8_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                            const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
-                            int N, int K, int64_t ldy, int out_f32, int splits, int n_tiles,
-                            int m_tiles, int group_m, const float* __restrict__ xscale,
-                            const float* __restrict__ wscale, int wscale_stride) {
-  gemm_2sm_body<BLOCK_X, EPI, 1>(tmap_w, tmap_x, Yv, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles,
+                            const __grid_constant__ CUtensorMap tmap_x,
+                            const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
+                            int splits, int n_tiles, int m_tiles, int group_m,
+                            const float* __restrict__ xscale, const float* __restrict__ wscale,
+                            int wscale_stride) {
+  gemm_2sm_body<BLOCK_X, EPI, 1>(tmap_w, tmap_x, tmap_y, M, N, K, out_f32, splits, n_tiles, m_tiles,
                                  group_m, xscale, wscale, wscale_stride);
 }
 
@@ -514,12 +534,24 @@ gemm_fp8_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
 template <int BLOCK_X, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_grouped_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                             const __grid_constant__ CUtensorMap tmap_x, void* __restrict__ Yv, int M,
-                             int N, int K, int64_t ldy, int n_tiles, int m_tiles, int group_m,
-                             const float* __restrict__ row_scale, const int32_t* __restrict__ tile_expert,
+                             const __grid_constant__ CUtensorMap tmap_x,
+                             const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int n_tiles,
+                             int m_tiles, int group_m, const float* __restrict__ row_scale,
+                             const int32_t* __restrict__ tile_expert,
                              const int32_t* __restrict__ num_m_tiles) {
-  gemm_2sm_body<BLOCK_X, EPI, 0, 1>(tmap_w, tmap_x, Yv, M, N, K, ldy, 0, 1, n_tiles, m_tiles, group_m,
+  gemm_2sm_body<BLOCK_X, EPI, 0, 1>(tmap_w, tmap_x, tmap_y, M, N, K, 0, 1, n_tiles, m_tiles, group_m,
                                     row_scale, nullptr, 0, GroupInfo{tile_expert, num_m_tiles});
+}
+
+// Tensor map of the output for the epilogue's TMA stores: [splits][M][N] (bf16, or fp32 when out_f32)
+// or, for the fused SiLU*mul epilogue, the [M][N/2] bf16 activation; box = one warp's chunk.
+template <int BLOCK_X, int EPI>
+static int make_out_tmap(CUtensorMap* ty, void* Y, int M, int N, int64_t ldy, int out_f32, int splits) {
+  constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
+  if constexpr (EPI == 1)
+    return make_tmap_out_3d(ty, Y, 2, (uint64_t)(N / 2), (uint64_t)M, 1, (uint64_t)ldy, 0, 16, CH);
+  return make_tmap_out_3d(ty, Y, out_f32 ? 4 : 2, (uint64_t)N, (uint64_t)M, (uint64_t)splits, (uint64_t)ldy,
+                          (uint64_t)M * (uint64_t)ldy, 32, CH);
 }
 
 static int g_gemm_multicast = -1;  // -1: read B200_GEMM_MULTICAST once (default on)
@@ -546,6 +578,9 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
     }
     attr_set = true;
   }
+  CUtensorMap ty;
+  const int rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
   const int n_units = (n_tiles + MC - 1) / MC;
@@ -555,7 +590,7 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
   const int clusters = total < max_clusters ? total : max_clusters;
   const int group_m = m_tiles < 8 ? m_tiles : 8;
   cudaError_t e = launch_pdl(kernel, dim3(clusters * MC), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, MC,
-                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
+                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -565,14 +600,24 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
 }
 
 // m-tiles per raster group: a group's activation tiles stay L2-resident while the weight matrix
-// streams past once per group (B200_GEMM_GROUP_M overrides for experiments).
-static int gemm_group_m(int m_tiles) {
+// streams past once per group (B200_GEMM_GROUP_M overrides for experiments).  16 tiles measured best
+// on the K = 4096 prefill shapes (16 x 256 tokens x 8 KB = 32 MB of activations); for long K the
+// group is shrunk so that its activation rows stay below ~64 MB -- a 16-tile group of the down
+// projection (K = 14336) is 117 MB, does not fit the 126 MB L2 next to the weights, and round 1
+// measured 3.1x the algorithmic DRAM traffic for it.
+static int gemm_group_m(int m_tiles, int K) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200_GEMM_GROUP_M");
-    v = (e && atoi(e) > 0) ? atoi(e) : 16;   // measured: 16 > 8 > 32 on the 8B prefill shapes
+    v = (e && atoi(e) > 0) ? atoi(e) : 0;
   }
-  return m_tiles < v ? m_tiles : v;
+  int g = v;
+  if (g <= 0) {
+    g = 16;
+    const long long tile_bytes = 256LL * (long long)K * 2;   // one m-tile of activations (bf16 element count)
+    while (g > 4 && (long long)g * tile_bytes > (64LL << 20)) g >>= 1;
+  }
+  return m_tiles < g ? m_tiles : g;
 }
 
 static bool gemm_2sm_enabled() {
@@ -603,14 +648,17 @@ static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
   if (rc) return rc;
+  CUtensorMap ty;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
   const int total = ((n_tiles + 1) / 2) * m_tiles * splits;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
-  const int group_m = gemm_group_m(m_tiles);
+  const int group_m = gemm_group_m(m_tiles, K);
   cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
-                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m);
+                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_bf16(2sm): launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -639,14 +687,17 @@ static int launch_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, 
   if (rc) return rc;
   rc = make_tmap_u8_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, 2 * kBlockK);
   if (rc) return rc;
+  CUtensorMap ty;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
   const int total = ((n_tiles + 1) / 2) * m_tiles * splits;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
-  const int group_m = gemm_group_m(m_tiles);
+  const int group_m = gemm_group_m(m_tiles, K / 2);   // a k-block is 128 one-byte elements
   cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
-                             tw, tx, Y, M, N, K, ldy, out_f32, splits, n_tiles, m_tiles, group_m, xscale, wscale,
+                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m, xscale, wscale,
                              wscale_stride);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_fp8: launch failed: %s", cudaGetErrorString(e));
@@ -845,14 +896,17 @@ static int launch_gemm_grouped(const void* X, const void* W, void* Y, int M, int
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
   if (rc) return rc;
+  CUtensorMap ty;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, 0, 1);
+  if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;      // capacity; the kernel clamps to the tiles in use
   const int total = ((n_tiles + 1) / 2) * m_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
-  const int group_m = gemm_group_m(m_tiles);
+  const int group_m = gemm_group_m(m_tiles, K);
   cudaError_t e = launch_pdl_cls(kPdlMoe, kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes,
-                                 stream, 2, tw, tx, Y, M, N, K, ldy, n_tiles, m_tiles, group_m, row_scale,
+                                 stream, 2, tw, tx, ty, M, N, K, n_tiles, m_tiles, group_m, row_scale,
                                  tile_expert, num_m_tiles);
   if (e != cudaSuccess) {
     b200_set_error("b200_moe_grouped_gemm: launch failed: %s", cudaGetErrorString(e));

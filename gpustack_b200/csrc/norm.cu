@@ -51,19 +51,19 @@ rms_norm_kernel(const bf16* __restrict__ x, const float* __restrict__ partials, 
         for (int s = 0; s < splits; ++s) {
           const float4* p =
               reinterpret_cast<const float4*>(partials + (size_t)s * T * H + off);
-          float4 a = __ldg(p), b = __ldg(p + 1);
+          float4 a = ld_cg_f4(p), b = ld_cg_f4(p + 1);   // written by the split-K GEMM just before
           v[i][0] += a.x; v[i][1] += a.y; v[i][2] += a.z; v[i][3] += a.w;
           v[i][4] += b.x; v[i][5] += b.y; v[i][6] += b.z; v[i][7] += b.w;
         }
       } else {
-        uint4 xa = ld_nc_v4(x + off);
+        uint4 xa = ld_cg_v4(x + off);
         v[i][0] = bf16_lo(xa.x); v[i][1] = bf16_hi(xa.x);
         v[i][2] = bf16_lo(xa.y); v[i][3] = bf16_hi(xa.y);
         v[i][4] = bf16_lo(xa.z); v[i][5] = bf16_hi(xa.z);
         v[i][6] = bf16_lo(xa.w); v[i][7] = bf16_hi(xa.w);
       }
       if (MODE != 0 && residual != nullptr) {
-        uint4 ra = ld_nc_v4(residual + off);
+        uint4 ra = ld_cg_v4(residual + off);
         v[i][0] += bf16_lo(ra.x); v[i][1] += bf16_hi(ra.x);
         v[i][2] += bf16_lo(ra.y); v[i][3] += bf16_hi(ra.y);
         v[i][4] += bf16_lo(ra.z); v[i][5] += bf16_hi(ra.z);

@@ -27,14 +27,14 @@ template <bool PARTIALS>
 __device__ __forceinline__ void load8(const bf16* qkv, const float* partials, int splits, size_t plane,
                                       size_t off, float (&f)[8], const bf16* bias = nullptr, int col = 0) {
   if constexpr (!PARTIALS) {
-    unpack8(ld_v4(qkv + off), f);
+    unpack8(ld_cg_v4(qkv + off), f);
     return;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = 0.f;
   for (int s = 0; s < splits; ++s) {
     const float4* p = reinterpret_cast<const float4*>(partials + (size_t)s * plane + off);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const float4 a = ld_cg_f4(p), b = ld_cg_f4(p + 1);
     f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
     f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
   }

@@ -63,14 +63,12 @@ bool pdl_enabled() {
 bool pdl_class_enabled(int cls) {
   static int off = -1;
   if (off < 0) {
-    // Default: the MoE routing kernels and grouped GEMMs are launched fully serialised.  Measured on
-    // B200 (tools/debug_moe_graph.py): with them launched as programmatic dependents, CUDA-graph
-    // replays of the tiny Mixtral decode step compute different logits for one sequence from the
-    // second decode step on, deterministically (eager launches, and graphs with this class
-    // serialised, are correct; so are the dense graphs) -- see DESIGN.md section 9.
-    // Their successors still overlap with them; B200_PDL_OFF_CLASSES=0 re-enables for experiments.
+    // Every class is a programmatic dependent by default.  (Round 1 had to serialise the MoE class:
+    // with the entry-time trigger, CUDA-graph replays of the tiny Mixtral decode step computed wrong
+    // logits -- DESIGN.md section 9.  The late trigger in common.cuh removes the cause; the knob
+    // B200_PDL_OFF_CLASSES=<bitmask> stays for experiments.)
     const char* e = getenv("B200_PDL_OFF_CLASSES");
-    off = e ? atoi(e) : (int)kPdlMoe;
+    off = e ? atoi(e) : 0;
   }
   return cls == 0 || (off & cls) == 0;
 }
@@ -131,6 +129,38 @@ static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
     b200_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows %llu cols %llu ld %llu box %ux%u)",
                    (int)r, (unsigned long long)rows, (unsigned long long)cols,
                    (unsigned long long)ld_elems, box_rows, box_cols);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+int make_tmap_out_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                     uint64_t planes, uint64_t ld_elems, uint64_t plane_elems, uint32_t box_cols,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    b200_set_error("cuTensorMapEncodeTiled entry point not available");
+    return B200_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld_elems * elem_bytes) & 15) ||
+      ((box_cols * elem_bytes) & 15)) {
+    b200_set_error("TMA store target must be 16-byte aligned (base %p, row pitch %llu B, box %u B)", base,
+                   (unsigned long long)(ld_elems * elem_bytes), box_cols * elem_bytes);
+    return B200_ERR_INVALID;
+  }
+  if (planes < 1) planes = 1;
+  if (plane_elems == 0) plane_elems = rows * ld_elems;
+  cuuint64_t dims[3] = {cols, rows, planes};
+  cuuint64_t strides[2] = {ld_elems * elem_bytes, plane_elems * elem_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200_set_error("cuTensorMapEncodeTiled(out) failed: CUresult %d (cols %llu rows %llu planes %llu ld %llu box %ux%u)",
+                   (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)planes,
+                   (unsigned long long)ld_elems, box_cols, box_rows);
     return B200_ERR_CUDA;
   }
   return B200_OK;

@@ -24,6 +24,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                     uint32_t box_rows, uint32_t box_cols);
 
+// 3-D, un-swizzled map used by the GEMM epilogues' TMA STORES: tensor [planes][rows][cols] of
+// elem_bytes-wide elements (2 = bf16, 4 = fp32), row pitch ld_elems, plane pitch plane_elems
+// (split-K partial planes; 1 plane otherwise); box = box_cols x box_rows x 1.  The hardware clips
+// the part of a box that lies outside [cols, rows, planes], so tail tiles need no predicates.
+int make_tmap_out_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                     uint64_t planes, uint64_t ld_elems, uint64_t plane_elems, uint32_t box_cols,
+                     uint32_t box_rows);
+
 // B200_PDL=0 disables programmatic dependent launch (default on).
 bool pdl_enabled();
 

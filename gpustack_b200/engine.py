@@ -122,15 +122,25 @@ class TPContext:
         self.nccl = dist.group.WORLD
         self.cpu = dist.new_group(backend="gloo")   # bootstrap / barriers; fallback step channel
         self.shm: Optional[ShmStepChannel] = None
-        if os.environ.get("B200_TP_STEP_CHANNEL", "shm") == "shm":
+
+    def open_step_channel(self, capacity_words: int) -> None:
+        """Shared-memory step channel sized for the largest step payload of this engine (so an
+        oversized step can never surface in the middle of serving).  The fence-free protocol relies
+        on x86 store ordering: on other hosts (aarch64 Grace) the gloo broadcast is used instead."""
+        import platform
+
+        dist = self.dist
+        want = os.environ.get("B200_TP_STEP_CHANNEL", "shm") == "shm" and platform.machine() in ("x86_64", "AMD64")
+        if want:
             try:
-                self.shm = ShmStepChannel(rank, world, dist, self.cpu)
+                self.shm = ShmStepChannel(self.rank, self.world, dist, self.cpu, capacity_words=capacity_words)
             except Exception:  # noqa: BLE001  (no /dev/shm, ...): gloo still works
                 self.shm = None
-            ok = torch.tensor([1 if self.shm is not None else 0])
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.cpu)
-            if int(ok[0]) == 0:
-                self.shm = None
+        ok = torch.tensor([1 if self.shm is not None else 0])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.cpu)
+        if int(ok[0]) == 0 and self.shm is not None:
+            self.shm.close()
+            self.shm = None
 
     @staticmethod
     def from_env() -> Optional["TPContext"]:
@@ -178,6 +188,10 @@ class LLMEngine:
                         mcfg.sliding_window)
             ecfg.max_model_len = mcfg.sliding_window
         self.runner = ModelRunner(mcfg, ecfg, weights, device=device, tp_group=tp.nccl if tp else None, tp_ctx=tp)
+        if tp and tp.shm is None:
+            r = self.runner
+            # largest payloads: decode = B*(2+max_blocks); prefill = 4*S + S*max_blocks + T
+            tp.open_step_channel(r.max_seqs * (r.max_blocks + 4) + r.max_tokens + 4096)
         n = self.runner.profile_num_blocks()
         if tp:   # every rank must use the same block count
             t = torch.tensor([n], dtype=torch.int64)

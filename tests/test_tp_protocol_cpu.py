@@ -41,6 +41,7 @@ def _worker(rank, port, q):
 
     dist.init_process_group(backend="gloo", rank=rank, world_size=2)
     tp = E.TPContext(rank, 2, torch.device("cpu"))
+    tp.open_step_channel(1 << 16)
     eng = E.LLMEngine.__new__(E.LLMEngine)      # protocol only: no GPU objects
     eng.tp, eng.runner = tp, FakeRunner()
     torch.cuda.synchronize = lambda *a, **k: None
@@ -94,7 +95,14 @@ def _stress(rank, port, q, channel):
 
     dist.init_process_group(backend="gloo", rank=rank, world_size=2)
     tp = E.TPContext(rank, 2, torch.device("cpu"))
+    tp.open_step_channel(8192)                  # sized by the engine from max_num_seqs / max_model_len
     assert (tp.shm is not None) == (channel == "shm")
+    if tp.shm is not None and rank == 0:        # an oversized payload is refused, never truncated
+        try:
+            tp.shm.send([0], np.zeros(8193, dtype=np.int32)); ok_big = False
+        except E.B200Error:
+            ok_big = True
+        assert ok_big
     rs = np.random.RandomState(0)
     ok, n_steps = True, 1500
     for i in range(n_steps):
