@@ -56,6 +56,13 @@ def parse_args():
                     help="fp8 = W8A8 side measurement (NOT the BASELINE config, which is bf16)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the HTTP end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-probe", action="store_true",
+                    help="skip the correctness probe (2-layer Llama-3-8B-width model vs the CPU oracle) run before timing")
+    ap.add_argument("--gpu-baseline", default="auto", choices=["auto", "on", "off"],
+                    help="time the reference GPU engine (vLLM, tools/vllm_baseline.py) on the same workload in the "
+                         "same lease; auto = at TP 1 and 8 when the time budget allows")
+    ap.add_argument("--time-budget-s", type=float, default=float(os.environ.get("B200_BENCH_BUDGET_S", "780")),
+                    help="wall-clock budget of the whole run; optional legs are skipped / bounded to stay inside it")
     ap.add_argument("--cpu-sample-requests", type=int, default=2)
     ap.add_argument("--cpu-sample-output", type=int, default=16)
     return ap.parse_args()
@@ -224,6 +231,224 @@ def free_port():
         return s.getsockname()[1]
 
 
+# ------------------------------------------------------------------------------------ parity probe
+PROBE_TOL = 2e-2   # relative to max|logit|: the engine-level tolerance of tests/test_engine_gpu.py
+
+
+def parity_probe(a, rank, world):
+    """Correctness of the EXACT code path that is about to be timed, at BASELINE width: a 2-layer
+    Llama-3-8B-shaped model (H 4096, I 14336, 32/8 heads of 128, vocab 32768; the same tile shapes,
+    split plans and -- under TP -- all-reduce paths as the benchmark model) generates 16 greedy
+    tokens for 8 seeded prompts; the CPU oracle is teacher-forced on the engine's tokens and every
+    step whose oracle top-2 margin exceeds the tolerance must agree.  Run twice: 8 sequences, and
+    256 concurrent sequences (decode batch 256 = the benchmark's batch, which under TP takes the
+    large-message all-reduce path) of which the same 8 are checked.  Every rank takes part."""
+    import torch
+
+    from gpustack_b200.config import EngineConfig, ModelConfig
+    from gpustack_b200.engine import LLMEngine, TPWorker
+    from gpustack_b200.scheduler import SamplingParams
+    from gpustack_b200.weights import random_state_dict
+
+    mcfg = ModelConfig(vocab_size=32768, hidden_size=4096, intermediate_size=14336, num_hidden_layers=2,
+                       num_attention_heads=32, num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5,
+                       rope_theta=500000.0, max_position_embeddings=1024, eos_token_id=2, bos_token_id=1)
+    device = f"cuda:{torch.cuda.current_device()}"
+    t0 = time.perf_counter()
+    runs, oracle = [], None
+    import numpy as np
+
+    rs = np.random.RandomState(4242)
+    checked_prompts = [rs.randint(3, mcfg.vocab_size, size=n).tolist() for n in (33, 64, 100, 128, 200, 17, 256, 77)]
+    filler = [rs.randint(3, mcfg.vocab_size, size=48).tolist() for _ in range(248)]
+    for max_seqs in (8, 256):
+        sd = random_state_dict(mcfg, seed=7, device=device)
+        if rank == 0 and oracle is None:
+            from oracle import llama_oracle as O   # the checker; never on the timed path
+
+            oc = O.LlamaConfig(vocab_size=mcfg.vocab_size, hidden_size=mcfg.hidden_size,
+                               intermediate_size=mcfg.intermediate_size, num_hidden_layers=mcfg.num_hidden_layers,
+                               num_attention_heads=mcfg.num_attention_heads,
+                               num_key_value_heads=mcfg.num_key_value_heads, head_dim=mcfg.head_dim,
+                               rms_norm_eps=mcfg.rms_norm_eps, rope_theta=mcfg.rope_theta,
+                               max_position_embeddings=mcfg.max_position_embeddings)
+            torch.set_num_threads(host_threads())
+            oracle = O.OracleLlama(oc, {k: v.cpu() for k, v in sd.items()}, fp32_cache=True)
+        ecfg = EngineConfig(model="random:probe", tensor_parallel_size=world, max_num_seqs=max_seqs,
+                            max_num_batched_tokens=4096, max_model_len=512, num_gpu_blocks=8192,
+                            enable_prefix_caching=False, seed=7,
+                            cuda_graph_sizes=[1, 2, 4, 8] + ([128, 256] if max_seqs == 256 else []))
+        eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict=sd)
+        del sd
+        if rank != 0:
+            TPWorker(eng).serve_forever()
+            del eng
+            torch.cuda.empty_cache()
+            continue
+        prompts = checked_prompts + (filler if max_seqs == 256 else [])
+        outs = eng.generate(prompts, SamplingParams(max_tokens=16, ignore_eos=True))
+        n_chk = n_ok = 0
+        for i, (p, o) in enumerate(zip(checked_prompts, outs[:len(checked_prompts)])):
+            oracle.reset()
+            logits = oracle.forward(i, p, last_only=True)[-1]
+            for t in range(len(o)):
+                top2 = torch.topk(logits, 2).values
+                if float(top2[0] - top2[1]) > PROBE_TOL * float(logits.abs().max()):
+                    n_chk += 1
+                    n_ok += int(int(torch.argmax(logits)) == int(o[t]))
+                logits = oracle.forward(i, [int(o[t])], last_only=True)[-1]
+        runs.append({"max_num_seqs": max_seqs, "concurrent": len(prompts), "checked": n_chk, "agree": n_ok,
+                     "decode_steps": eng.runner.stats["decode_steps"]})
+        eng.shutdown()
+        del eng
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    del oracle
+    return {"tp": world, "model": "2-layer Llama-3-8B width (H4096 I14336 32/8x128 V32768), seeded N(0,0.02)",
+            "protocol": "8 prompts x 16 greedy tokens, CPU oracle teacher-forced on the engine's tokens, steps with "
+                        f"top-2 margin > {PROBE_TOL} x max|logit| must agree",
+            "checked": sum(r["checked"] for r in runs), "agree": sum(r["agree"] for r in runs), "runs": runs,
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
+# ------------------------------------------------------------------------------------ reference GPU engine
+def gpu_baseline(a, budget_s):
+    """vLLM (the engine GPUStack's own backend launches) on the same workload, same lease, same
+    step counts: tools/vllm_baseline.py in a fresh process (no torchrun environment), bounded by
+    what is left of the time budget.  Returns a dict (with "error" when it could not be measured)."""
+    env = {k: v for k, v in os.environ.items()
+           if not (k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE",
+                         "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS",
+                         "NCCL_DEBUG", "NCCL_DEBUG_FILE", "NCCL_ASYNC_ERROR_HANDLING")
+                   or k.startswith("TORCHELASTIC") or k.startswith("TORCH_NCCL"))}
+    env["VLLM_LOGGING_LEVEL"] = "INFO"
+    cmd = [sys.executable, str(ROOT / "tools" / "vllm_baseline.py"), str(a.requests), str(a.steps), "--tp", str(a.gpus),
+           "--warmup", str(min(a.warmup, 2)), "--input-len", str(a.input_len), "--output-len", str(a.output_len)]
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=max(60.0, budget_s), env=env, cwd=str(ROOT))
+    except subprocess.TimeoutExpired:
+        return {"engine": "vllm", "error": f"timed out after {budget_s:.0f}s (start-up + {a.steps} steps did not fit the budget)"}
+    except Exception as e:  # noqa: BLE001
+        return {"engine": "vllm", "error": repr(e)[:300]}
+    out = None
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith("{"):
+            try:
+                out = json.loads(line)
+                break
+            except ValueError:
+                continue
+    if r.returncode != 0 or out is None:
+        return {"engine": "vllm", "error": f"rc={r.returncode}: " + (r.stderr or r.stdout)[-400:].replace("\n", " | ")}
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        from vllm_baseline import parse_backend_log
+
+        out.update({k: v for k, v in parse_backend_log(r.stdout + r.stderr).items() if v})
+    except Exception:  # noqa: BLE001
+        pass
+    out.pop("steps", None)
+    out["wall_s"] = round(time.perf_counter() - t0, 1)
+    out["same_lease"] = True
+    return out
+
+
+def gpus_idle(n, limit_mib=4000, wait_s=30.0):
+    """True once the first n GPUs hold less than limit_mib each (the other ranks have exited)."""
+    t0 = time.time()
+    while time.time() - t0 < wait_s:
+        try:
+            r = subprocess.run(["nvidia-smi", "--query-gpu=memory.used", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10)
+            used = [int(x) for x in r.stdout.split()[:n]]
+            if used and max(used) < limit_mib:
+                return True
+        except Exception:  # noqa: BLE001
+            return True
+        time.sleep(1.0)
+    return False
+
+
+def micro_rooflines(engine, a, mcfg, pk):
+    """Device-timed (CUDA events, eager launches, weights of all layers rotate through HBM) roofline
+    entries for the kernels that the dominant-kernel `roofline` would otherwise hide: the
+    decode-shaped projections at M = batch, and prefill attention on a 16 x 512-token batch."""
+    import torch
+
+    from gpustack_b200 import ops
+
+    run, w = engine.runner, engine.runner.w
+    if run.fp8 or mcfg.num_local_experts:
+        return {}
+    M = min(a.requests, run.max_seqs)
+    x = run.xn[:M]
+    act = run.act[:M]
+    res = {}
+
+    def layer_pass():
+        for lw in w.layers:
+            ops.gemm(x, lw.qkv, out=run.qkv[:M])
+            ops.gemm(run.attn_out[:M], lw.o, out=run.hbuf[:M])
+            ops.gemm_silu_mul(x, lw.gate_up, out=act)
+            ops.gemm(act, lw.down, out=run.hbuf[:M])
+
+    layer_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        layer_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    L = len(w.layers)
+    us_layer = e0.elapsed_time(e1) * 1e3 / (reps * L)
+    wbytes = sum(t.numel() * 2 for t in (w.layers[0].qkv, w.layers[0].o, w.layers[0].gate_up, w.layers[0].down))
+    flops = 2.0 * M * wbytes / 2
+    res["roofline_decode_gemm"] = {
+        "kernel": f"QKV + O + gate_up(SiLU) + down projections at M={M} (one decoder layer, 4 launches)",
+        "us_per_layer": us_layer, "bound": "hbm", "achieved": wbytes / (us_layer * 1e-6) / 1e9, "peak": pk["hbm_gbs"],
+        "unit": "GB/s", "frac": wbytes / (us_layer * 1e-6) / 1e9 / pk["hbm_gbs"],
+        "tensor_tflops": flops / (us_layer * 1e-6) / 1e12, "tensor_frac": flops / (us_layer * 1e-6) / 1e12 / pk["bf16_tflops"],
+        "algorithmic_bytes_per_layer": wbytes, "timing": "CUDA events around 3 x 32-layer eager passes (PDL launches)"}
+    # prefill attention: 16 sequences x 512 tokens, causal, through the engine's own prefill path inputs
+    S, n = max(1, min(16, run.max_tokens // a.input_len)), a.input_len
+    if run.num_blocks > S * (n // run.block_size + 1) + 1:
+        T = S * n
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=run.device)   # noqa: E731
+        bpp = n // run.block_size + 1
+        bt = torch.zeros(S, run.max_blocks, dtype=torch.int32, device=run.device)
+        for s_ in range(S):
+            bt[s_, :bpp] = torch.arange(1 + s_ * bpp, 1 + (s_ + 1) * bpp, dtype=torch.int32)
+        ts, tq = ops.build_prefill_tiles([n] * S, run.prefill_tile)
+        cu, ctx, ts_d, tq_d = i32([i * n for i in range(S + 1)]), i32([0] * S), i32(ts), i32(tq)
+        run.qkv[:T].normal_()
+
+        def attn(l):
+            ops.paged_attn_prefill(run.qkv[:T], run.qkv_width, run.k_cache[l], run.v_cache[l], bt, cu, ctx, ts_d, tq_d,
+                                   run.attn_out[:T], run.Hq, run.Hkv, run.D, run.scale)
+
+        for l in range(min(4, L)):
+            attn(l)
+        torch.cuda.synchronize()
+        e0.record()
+        for l in range(L):
+            attn(l)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / L
+        fl = 4.0 * S * (n * (n + 1) / 2) * run.Hq * run.D
+        res["roofline_prefill_attn"] = {
+            "kernel": "paged_attn_prefill (tcgen05/TMEM FMHA for head_dim 128, GQA 4|8)", "us_per_launch": us,
+            "bound": "tensor", "achieved": fl / (us * 1e-6) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": fl / (us * 1e-6) / 1e12 / pk["bf16_tflops"], "flops_per_launch": fl,
+            "shape": f"{S} x {n} tokens causal, Hq {run.Hq} / Hkv {run.Hkv} x {run.D}",
+            "peak_source": f"{pk['source']} (burst cuBLAS bf16: kernel timed alone)"}
+    return res
+
+
 def run_http_leg(engine, a, mcfg, n_warm, n_timed):
     """Serve the SAME engine over HTTP exactly as `b200-engine serve` does -- this process keeps
     running the engine-core busy loop (on a thread here, bench.py's main thread drives the client),
@@ -284,13 +509,20 @@ def run_ours(a):
     from gpustack_b200.engine import LLMEngine, TPWorker
     from gpustack_b200.scheduler import SamplingParams
 
-    os.environ.pop("NCCL_DEBUG", None)   # NCCL's version banner goes to stdout; keep it to the JSON line
+    # NCCL_DEBUG is left as the launcher set it (the communicator log is the driver's evidence of the
+    # rank count); the JSON line is printed LAST, after the process group is gone.
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world != a.gpus:
         raise SystemExit(f"--gpus {a.gpus} needs one process per GPU (WORLD_SIZE={world}); launch with "
                          "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    parity = None
+    if not a.no_parity_probe:
+        tpp = time.perf_counter()
+        parity = parity_probe(a, rank, world)
+        if rank == 0:
+            log(f"parity probe ({time.perf_counter() - tpp:.1f}s): {parity}")
     mcfg = model_config(a.model)
     ecfg = EngineConfig(model=f"random:{a.model}", tensor_parallel_size=a.gpus, max_num_seqs=a.requests,
                         max_num_batched_tokens=a.max_num_batched_tokens,
@@ -304,7 +536,7 @@ def run_ours(a):
     log(f"rank {rank}: engine ready in {init_s:.1f}s, {engine.num_blocks} KV blocks, graphs {len(engine.runner.graphs)}")
     if rank != 0:
         TPWorker(engine).serve_forever()
-        return
+        return None
     sp = SamplingParams(max_tokens=a.output_len, ignore_eos=True)
     R, K, W = a.requests, a.steps, a.warmup
 
@@ -394,10 +626,16 @@ def run_ours(a):
             log(f"e2e: {res['e2e']}")
         except Exception as e:  # noqa: BLE001
             res["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
-    engine.shutdown()
+    if parity is not None:
+        res["tp_parity"] = parity
+    engine.shutdown()                      # the other ranks leave serve_forever and exit
+    try:
+        res.update(micro_rooflines(engine, a, mcfg, pk))
+    except Exception as e:  # noqa: BLE001
+        res["roofline_decode_gemm"] = {"error": repr(e)[:200]}
+    del engine
+    torch.cuda.empty_cache()
     if a.gpus == 1 and not a.no_cpu_baseline:
-        del engine
-        torch.cuda.empty_cache()
         log("CPU baseline (oracle port) ...")
         v, t, dt = cpu_reference(a.model, a.cpu_sample_requests, a.input_len, a.cpu_sample_output)
         log(f"cpu baseline {v:.2f} tok/s in {dt:.1f}s")
@@ -405,15 +643,41 @@ def run_ours(a):
                                "p50_ttft_ms": t,
                                "sample": f"{a.cpu_sample_requests} requests x {a.input_len} in / {a.cpu_sample_output} out, "
                                          f"sequential, {dt:.1f} s of CPU work (oracle/llama_oracle.py, fp32 math)"}
-    print(json.dumps(res))
+    return res
+
+
+def finish_ours(a, res):
+    """Runs on rank 0 after the process group is destroyed: the same-lease reference-GPU-engine leg,
+    then the ONE JSON line, last on stdout."""
+    want = a.gpu_baseline == "on" or (a.gpu_baseline == "auto" and a.gpus in (1, 8) and a.model == "llama3-8b"
+                                      and a.quantization is None)
+    if want:
+        left = a.time_budget_s - (time.time() - _T0)
+        if left < 240 and a.gpu_baseline != "on":
+            res["gpu_baseline"] = {"engine": "vllm", "error": f"skipped: {left:.0f}s of the {a.time_budget_s:.0f}s budget left"}
+        elif not gpus_idle(a.gpus):
+            res["gpu_baseline"] = {"engine": "vllm", "error": "skipped: the GPUs were still in use by exiting ranks"}
+        else:
+            log(f"reference GPU engine (vLLM, TP={a.gpus}), {left:.0f}s of budget left ...")
+            res["gpu_baseline"] = gpu_baseline(a, left - 20.0)
+            log(f"gpu_baseline: {res['gpu_baseline']}")
+        gb = res["gpu_baseline"]
+        if gb.get("output_tok_s"):
+            gb["ours_over_baseline"] = res["value"] / gb["output_tok_s"]
+    sys.stdout.flush()
+    print(json.dumps(res), flush=True)
+    bad = res.get("tp_parity") and res["tp_parity"]["agree"] != res["tp_parity"]["checked"]
+    if bad:
+        log("PARITY PROBE FAILED: " + json.dumps(res["tp_parity"]))
+    return 1 if bad else 0
 
 
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
-    else:
-        run_ours(a)
+        return 0
+    res = run_ours(a)
     try:
         import torch.distributed as dist
 
@@ -421,7 +685,12 @@ def main():
             dist.destroy_process_group()
     except Exception:
         pass
+    if res is None:          # ranks > 0
+        return 0
+    if a.gpus > 1:
+        time.sleep(2.0)      # let the other ranks' last NCCL / torchrun lines drain before the JSON line
+    return finish_ours(a, res)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

@@ -24,6 +24,7 @@ SOURCES = [
     "quant_fp8.cu",
     "moe.cu",
     "attention.cu",
+    "attention_prefill_tc.cu",
     "allreduce.cu",
 ]
 NVCC_FLAGS = [

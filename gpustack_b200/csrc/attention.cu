@@ -747,8 +747,17 @@ extern "C" int b200_attn_prefill_tile(int Hq, int Hkv) {
   return G <= 4 ? 32 : 16;
 }
 
-extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache,
-                                       const void* v_cache, const int32_t* block_table,
+namespace b200 {
+// attention_prefill_tc.cu: tcgen05 / TMEM kernel (D = 128, GQA group of 4 or 8); returns 1 when the
+// configuration is not covered
+int paged_attn_prefill_tc(const void* q, int64_t q_stride, int num_tokens, const void* k_cache, const void* v_cache,
+                          int num_blocks, const int32_t* block_table, int max_blocks, const int32_t* cu_q,
+                          const int32_t* ctx_lens, const int32_t* tile_seq, const int32_t* tile_q0, int num_tiles,
+                          void* out, int Hq, int Hkv, int D, float scale, cudaStream_t stream);
+}  // namespace b200
+
+extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, int num_tokens, const void* k_cache,
+                                       const void* v_cache, int num_blocks, const int32_t* block_table,
                                        int max_blocks, const int32_t* cu_q,
                                        const int32_t* ctx_lens, const int32_t* tile_seq,
                                        const int32_t* tile_q0, int num_tiles, void* out, int Hq,
@@ -761,6 +770,13 @@ extern "C" int b200_paged_attn_prefill(const void* q, int64_t q_stride, const vo
   B200_REQUIRE(q_stride % 2 == 0, "attn_prefill: q_stride must be even");
   if (num_tiles <= 0) return B200_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    // tensor-core path first (the kernels below are the mma.sync fallback for other head shapes)
+    const int rc_tc = paged_attn_prefill_tc(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table,
+                                            max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv,
+                                            D, scale, s);
+    if (rc_tc <= 0) return rc_tc;
+  }
   const float scale_log2 = scale * 1.4426950408889634f;
   const int G = Hq / Hkv, QT = tile / 16;
   dim3 grid(num_tiles, Hkv);

@@ -1,0 +1,374 @@
+// Causal paged-KV prefill attention on the 5th-generation tensor cores (reference operator:
+// FlashInferImpl.forward -> trtllm_batch_context_with_kv_cache,
+// $VLLM/v1/attention/backends/flashinfer.py:1095-1230; on cc 10.x the reference engine runs
+// FlashInfer's TRT-LLM-gen FMHA cubins for this step).
+//
+// One CTA = one 128-row query tile of one (sequence, kv-head): the G = Hq/Hkv query heads that share
+// the kv-head times 128/G consecutive query tokens, so that S = Q K^T is a single UMMA M = 128 tile
+// and every K/V byte staged in shared memory serves the whole GQA group.
+//
+//   warp 4    TMA producer: the Q tile once, then K_j / V_j blocks of 64 tokens (4 KV pages of 16
+//             tokens, each page two 2 KB boxes of the 128-byte-swizzled layout) through a 4-slot
+//             mbarrier ring; pages past the end of the sequence are read from the all-zero null block;
+//   warp 5    MMA issuer (one elected thread): S_j = Q K_j^T into one of two 64-column TMEM buffers,
+//             O += P_j V_j into a 128-column TMEM accumulator.  S_{j+1} is issued BEFORE waiting for
+//             P_j, so the tensor pipe works on block j+1 while the softmax warps are busy with j;
+//   warps 0-3 softmax: thread = one query row (TMEM lane).  tcgen05.ld S, scale / causal mask,
+//             online softmax in base 2 with LAZY rescaling (the running reference maximum is only
+//             moved when the row maximum grows by more than 2^8, so the O accumulator in TMEM is
+//             rescaled rarely; P values stay <= 256, exact in fp32 / fine in bf16), P rounded to bf16
+//             into swizzled shared memory as the K-major A operand of the PV MMA; at the end
+//             O / l -> bf16 -> global.
+//
+// V is consumed as an MN-major B operand straight from its [token][d] page layout (no transpose).
+// Two CTAs share an SM (112 KB of shared memory, 256 TMEM columns each): one CTA's softmax / epilogue
+// overlaps the other's MMAs.  Work per launch: 4 * T * ctx/2 * Hq * D FLOP (tensor-bound).
+#include "common.cuh"
+#include "runtime.h"
+#include "../../include/b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace b200 {
+
+constexpr int kFaThreads = 192;
+constexpr int kFaD = 128;
+constexpr int kUmmaKBf16 = 16;                         // K elements per tcgen05.mma (kind::f16)
+constexpr int kFaKv = 64;                              // KV tokens per ring slot
+constexpr int kFaPage = 16;                            // tokens per KV page (vLLM block_size)
+constexpr int kFaSlotBytes = kFaKv * kFaD * 2;         // 16 KB = 2 d-halves x [64 tokens][128 B]
+constexpr int kFaHalfBytes = kFaKv * 128;              // 8 KB
+constexpr int kFaSlots = 4;                            // K_j, V_j, K_j+1, V_j+1
+constexpr int kFaQBytes = 128 * kFaD * 2;              // 32 KB = 2 d-halves x [128 rows][128 B]
+constexpr int kFaQHalfBytes = 128 * 128;               // 16 KB
+constexpr int kFaPBytes = 128 * kFaKv * 2;             // 16 KB = [128 rows][128 B]
+constexpr int kFaOffKV = kFaQBytes;
+constexpr int kFaOffP = kFaOffKV + kFaSlots * kFaSlotBytes;
+constexpr int kFaOffBar = kFaOffP + kFaPBytes;         // 114,688
+constexpr int kFaSmemBytes = 115712;                   // (228 KB - 2 x 1 KB reserved) / 2 CTAs per SM
+constexpr int kFaMaxSlack = kFaSmemBytes - kFaOffBar - 256;
+constexpr int kFaTmemCols = 256;                       // S0 [0,64)  S1 [64,128)  O [128,256)
+constexpr float kFaRescaleThreshold = 8.f;             // log2 units
+
+template <int G>
+__global__ void __launch_bounds__(kFaThreads, 2)
+paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                             const __grid_constant__ CUtensorMap tmap_k,
+                             const __grid_constant__ CUtensorMap tmap_v,
+                             const int32_t* __restrict__ block_table, int max_blocks,
+                             const int32_t* __restrict__ cu_q, const int32_t* __restrict__ ctx_lens,
+                             const int32_t* __restrict__ tile_seq, const int32_t* __restrict__ tile_q0,
+                             bf16* __restrict__ out, int Hq, int Hkv, float scale_log2) {
+  constexpr int TPT = 128 / G;   // query tokens per tile
+  extern __shared__ uint8_t fa_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  if (smem - fa_raw > kFaMaxSlack) __trap();   // the swizzled tiles need 1024-byte alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFaOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;     // [4]
+  uint64_t* kv_empty = bars + 5;    // [4]
+  uint64_t* s_full = bars + 9;      // [2]
+  uint64_t* p_full = bars + 11;
+  uint64_t* p_empty = bars + 12;
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kFaSlots; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 4);     // one arrive per softmax warp
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, kFaTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // Q, the KV cache and the index buffers were written by preceding kernels / copies
+
+  const int tile = blockIdx.x, kvh = blockIdx.y;
+  const int seq = tile_seq[tile], q0 = tile_q0[tile];
+  const int q_begin = cu_q[seq];
+  const int q_len = cu_q[seq + 1] - q_begin;
+  const int ctx = ctx_lens[seq];
+  const int total_len = ctx + q_len;
+  const int kv_end = min(total_len, ctx + q0 + TPT);       // causal horizon of the tile (exclusive)
+  const int n_blocks = (kv_end + kFaKv - 1) / kFaKv;       // >= 1
+  const int n_pages_seq = (total_len + kFaPage - 1) / kFaPage;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(q_full, kFaQBytes);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(smem + h * kFaQHalfBytes + g * TPT * 128, &tmap_q, q_full, (kvh * G + g) * kFaD + h * 64,
+                      q_begin + q0, kEvictFirst);
+      }
+      const int32_t* bt = block_table + (size_t)seq * max_blocks;
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_blocks; ++j) {
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {   // K_j then V_j
+          mbar_wait_guarded(&kv_empty[slot], phase ^ 1);
+          mbar_expect_tx(&kv_full[slot], kFaSlotBytes);
+          uint8_t* dst = smem + kFaOffKV + slot * kFaSlotBytes;
+#pragma unroll
+          for (int p = 0; p < kFaKv / kFaPage; ++p) {
+            const int page = j * (kFaKv / kFaPage) + p;
+            const int blk = page < n_pages_seq ? bt[page] : 0;   // block 0: the all-zero null block
+            const int row = (blk * Hkv + kvh) * kFaPage;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(dst + h * kFaHalfBytes + p * (kFaPage * 128), kv ? &tmap_v : &tmap_k, &kv_full[slot],
+                          h * 64, row, kEvictNormal);
+          }
+          if (++slot == kFaSlots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kFaKv);        // S[128 x 64]  = Q K^T
+      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kFaD);     // O[128 x 128] += P V (V MN-major)
+      const uint32_t q_addr = smem_u32(smem);
+      const uint32_t kv_addr = smem_u32(smem + kFaOffKV);
+      const uint32_t p_addr = smem_u32(smem + kFaOffP);
+      mbar_wait_guarded(q_full, 0);
+      tc_fence_after();
+      auto issue_s = [&](int j) {
+        const int slot = (2 * j) & 3;
+        mbar_wait_guarded(&kv_full[slot], ((2 * j) >> 2) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = kv_addr + slot * kFaSlotBytes;
+        const uint32_t d = tmem_base + (uint32_t)((j & 1) * kFaKv);
+#pragma unroll
+        for (int k = 0; k < kFaD / kUmmaKBf16; ++k) {   // 8 MMAs x 16 head-dim elements
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          umma_bf16(d, umma_desc_k_sw128(q_addr + half * kFaQHalfBytes + off),
+                    umma_desc_k_sw128(k_addr + half * kFaHalfBytes + off), idesc_s, k != 0);
+        }
+        umma_commit(&kv_empty[slot]);     // K_j slot reusable once these MMAs retire
+        umma_commit(&s_full[j & 1]);      // S_j ready for the softmax warps
+      };
+      issue_s(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        // S buffer (j+1)&1 held S_{j-1}, which the softmax warps finished reading before p_full(j-1)
+        if (j + 1 < n_blocks) issue_s(j + 1);
+        mbar_wait_guarded(p_full, j & 1);
+        tc_fence_after();
+        const int slot = (2 * j + 1) & 3;
+        mbar_wait_guarded(&kv_full[slot], ((2 * j + 1) >> 2) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = kv_addr + slot * kFaSlotBytes;
+#pragma unroll
+        for (int k = 0; k < kFaKv / kUmmaKBf16; ++k)     // 4 MMAs x 16 KV tokens
+          umma_bf16(tmem_base + 2 * kFaKv, umma_desc_k_sw128(p_addr + k * 32),
+                    umma_desc_mn_sw128(v_addr + k * (kUmmaKBf16 * 128), kFaHalfBytes, 1024), idesc_o, (j | k) != 0);
+        umma_commit(&kv_empty[slot]);     // V_j slot reusable
+        umma_commit(p_empty);             // P buffer and the O accumulator are stable again
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / epilogue (warps 0..3)
+    const int row = warp * 32 + lane;        // TMEM lane = tile row = (head g, token tok)
+    const int g = row / TPT, tok = row % TPT;
+    const int qi = q0 + tok;
+    const bool valid = qi < q_len;
+    const int qpos = ctx + qi;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t p_row = smem_u32(smem + kFaOffP) + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    float m_used = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait_guarded(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(t_lane + (uint32_t)((j & 1) * kFaKv), s0);
+      tmem_ld_32x32(t_lane + (uint32_t)((j & 1) * kFaKv + 32), s1);
+      tmem_ld_wait();
+      const int kv0 = j * kFaKv;
+      // block-uniform: does any row of the tile see a masked column in this block?
+      const bool need_mask = (kv0 + kFaKv - 1 > ctx + q0) || (kv0 + kFaKv - 1 >= total_len);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float a = __uint_as_float(s0[c]) * scale_log2;
+        float b = __uint_as_float(s1[c]) * scale_log2;
+        if (need_mask) {
+          const int ka = kv0 + c, kb = kv0 + 32 + c;
+          if (ka > qpos || ka >= total_len) a = -INFINITY;
+          if (kb > qpos || kb >= total_len) b = -INFINITY;
+        }
+        s0[c] = __float_as_uint(a);
+        s1[c] = __float_as_uint(b);
+        mx = fmaxf(mx, fmaxf(a, b));
+      }
+      // lazy rescale: move the reference maximum only when the row maximum outgrew it by > 2^8
+      // (always on the first block, where m_used = -inf and the factor is exp2(-inf) = 0)
+      float alpha = 1.f;
+      bool rescale = false;
+      if (mx > m_used + kFaRescaleThreshold) {
+        alpha = ex2_approx(m_used - mx);
+        m_used = mx;
+        l *= alpha;
+        rescale = j > 0;
+      }
+      uint32_t pk[32];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float p0 = ex2_approx(__uint_as_float(s0[c]) - m_used);
+        const float p1 = ex2_approx(__uint_as_float(s0[c + 1]) - m_used);
+        const float p2 = ex2_approx(__uint_as_float(s1[c]) - m_used);
+        const float p3 = ex2_approx(__uint_as_float(s1[c + 1]) - m_used);
+        sum += (p0 + p1) + (p2 + p3);
+        pk[c >> 1] = pack_bf16(p0, p1);
+        pk[16 + (c >> 1)] = pack_bf16(p2, p3);
+      }
+      l += sum;
+      if (j > 0) {   // PV_{j-1} has retired: P may be overwritten, O may be rescaled
+        mbar_wait_guarded(p_empty, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+        for (int c4 = 0; c4 < kFaD / 32; ++c4) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+        }
+        tmem_st_wait();
+      }
+      // P row (64 bf16 = 8 chunks of 16 B) into the 128B-swizzled K-major A-operand layout
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        st_shared_v4(p_row + (((uint32_t)ch ^ sw) << 4),
+                     make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> out[token, head, :]
+    mbar_wait_guarded(o_full, 0);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    bf16* orow = out + ((size_t)(q_begin + qi) * Hq + (size_t)(kvh * G + g)) * kFaD;
+#pragma unroll 1
+    for (int c4 = 0; c4 < kFaD / 32; ++c4) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[8 * v + 0]) * inv, __uint_as_float(o[8 * v + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv);
+          st_v4(orow + c4 * 32 + v * 8, w);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kFaTmemCols);
+  }
+}
+
+template <int G>
+static int launch_prefill_tc(const void* q, int64_t q_stride, int num_tokens, const void* k_cache,
+                             const void* v_cache, int num_blocks, const int32_t* block_table, int max_blocks,
+                             const int32_t* cu_q, const int32_t* ctx_lens, const int32_t* tile_seq,
+                             const int32_t* tile_q0, int num_tiles, void* out, int Hq, int Hkv, float scale,
+                             cudaStream_t stream) {
+  auto kernel = paged_attn_prefill_tc_kernel<G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      b200_set_error("attn_prefill(tc): cudaFuncSetAttribute(smem=%d): %s", kFaSmemBytes, cudaGetErrorString(e));
+      return B200_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_bf16_2d(&tq, q, (uint64_t)num_tokens, (uint64_t)Hq * kFaD, (uint64_t)q_stride, 128 / G, 64);
+  if (rc) return rc;
+  const uint64_t kv_rows = (uint64_t)num_blocks * (uint64_t)Hkv * kFaPage;
+  rc = make_tmap_bf16_2d(&tk, k_cache, kv_rows, kFaD, kFaD, kFaPage, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tv, v_cache, kv_rows, kFaD, kFaD, kFaPage, 64);
+  if (rc) return rc;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  cudaError_t e = launch_pdl(kernel, dim3(num_tiles, Hkv), dim3(kFaThreads), (size_t)kFaSmemBytes, stream, 1, tq, tk,
+                             tv, block_table, max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, (bf16*)out, Hq, Hkv,
+                             scale_log2);
+  if (e != cudaSuccess) {
+    b200_set_error("b200_paged_attn_prefill(tc): launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200_ERR_CUDA;
+  }
+  return b200_check_launch("b200_paged_attn_prefill(tc)");
+}
+
+// Called by b200_paged_attn_prefill (attention.cu).  Returns 1 when this kernel does not cover the
+// configuration (the caller then runs the mma.sync kernel), 0 on success, < 0 on error.
+int paged_attn_prefill_tc(const void* q, int64_t q_stride, int num_tokens, const void* k_cache, const void* v_cache,
+                          int num_blocks, const int32_t* block_table, int max_blocks, const int32_t* cu_q,
+                          const int32_t* ctx_lens, const int32_t* tile_seq, const int32_t* tile_q0, int num_tiles,
+                          void* out, int Hq, int Hkv, int D, float scale, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("B200_ATTN_PREFILL_TC");   // =0: keep the mma.sync kernels (A/B runs)
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int G = Hq / Hkv;
+  const DeviceInfo& d = device_info();
+  if (!enabled || D != kFaD || (G != 4 && G != 8) || !d.valid || d.cc_major != 10) return 1;
+  if (num_tokens <= 0 || num_blocks <= 0 || (q_stride % 8) != 0) return 1;
+  if (G == 4)
+    return launch_prefill_tc<4>(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table, max_blocks, cu_q,
+                                ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv, scale, stream);
+  return launch_prefill_tc<8>(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table, max_blocks, cu_q,
+                              ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv, scale, stream);
+}
+
+}  // namespace b200

@@ -83,10 +83,18 @@ __device__ __forceinline__ TileCoord decode_unit(int u, int n_tiles, int m_tiles
 //        scale xs[m] and the weight row's scale ws (already loaded by the caller) before any
 //        rounding, as cutlass_scaled_mm does in the reference engine.
 // n0: first output column (weight row) of this warp; `which` (in/out): staging buffer to fill next.
+// DirectOut: fallback for outputs whose row pitch is not a multiple of 16 bytes (a TMA tensor map
+// cannot describe them): plain per-thread stores, one element each -- correct, slow, and only ever
+// taken by odd-shaped test matrices (every tensor of the engine is 16-byte pitched).
+struct DirectOut {
+  void* ptr;      // nullptr: TMA-store path
+  int64_t ldy;
+};
+
 template <int BLOCK_X, int EPI, int FP8 = 0>
 __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, const CUtensorMap* tmap_y, uint8_t* stg,
                                                     int& which, int n0, int m_base, int split, int M, int N,
-                                                    int out_f32, int lane,
+                                                    int out_f32, int lane, DirectOut dir,
                                                     const float* __restrict__ xs = nullptr, float ws = 1.f) {
   constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -108,6 +116,32 @@ __device__ __forceinline__ void epilogue_store_tile(uint32_t t_addr, const CUten
 #pragma unroll
       for (int j = 0; j < CH; ++j)
         r[j] = __float_as_uint(__uint_as_float(r[j]) * (__shfl_sync(0xffffffffu, xs_lane, j) * ws));
+    }
+    if (dir.ptr != nullptr) {   // warp-uniform
+      const int n = n0 + lane;
+      if constexpr (EPI == 1) {
+        bf16* dst = reinterpret_cast<bf16*>(dir.ptr) + (size_t)(m_base + c0) * dir.ldy + (n >> 1);
+        const bool odd = lane & 1;
+#pragma unroll
+        for (int j = 0; j < CH; j += 2) {
+          const uint32_t send = odd ? r[j] : r[j + 1];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          const float g = round_bf16(__uint_as_float(odd ? recv : r[j]));
+          const float up = round_bf16(__uint_as_float(odd ? r[j + 1] : recv));
+          const float sg = round_bf16(g / (1.f + __expf(-g)));
+          const int m = m_base + c0 + j + (odd ? 1 : 0);
+          if (n < N && m < M) dst[(size_t)(j + (odd ? 1 : 0)) * dir.ldy] = __float2bfloat16_rn(sg * up);
+        }
+      } else if (n < N) {
+        const size_t off = ((size_t)split * M + (size_t)(m_base + c0)) * dir.ldy + n;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (m_base + c0 + j >= M) break;
+          if (out_f32) reinterpret_cast<float*>(dir.ptr)[off + (size_t)j * dir.ldy] = __uint_as_float(r[j]);
+          else reinterpret_cast<bf16*>(dir.ptr)[off + (size_t)j * dir.ldy] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+      }
+      continue;
     }
     uint8_t* buf = stg + which * kStgBufBytes;
     const uint32_t sbuf = smem_u32(buf);
@@ -164,7 +198,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_x,
                          const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
-                         int splits, int n_tiles, int m_tiles, int group_m) {
+                         int splits, int n_tiles, int m_tiles, int group_m, DirectOut dir) {
   using Cfg = GemmCfg<BLOCK_X>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -290,7 +324,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w,
       const int n0 = (c.n_tile * MC + (int)crank) * kBlockW + quad * 32;
       const int m_base = c.m_tile * BLOCK_X;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_X);
-      epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane);
+      epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane, dir);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -349,7 +383,7 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
                                               int out_f32, int splits, int n_tiles, int m_tiles,
                                               int group_m, const float* __restrict__ xscale,
                                               const float* __restrict__ wscale, int wscale_stride,
-                                              GroupInfo grp = GroupInfo{nullptr, nullptr}) {
+                                              DirectOut dir, GroupInfo grp = GroupInfo{nullptr, nullptr}) {
   using Cfg = Gemm2Cfg<BLOCK_X>;
   constexpr int kElemsK = FP8 ? 2 * kBlockK : kBlockK;   // elements per 128-byte k-block
   constexpr int STAGES = Cfg::kStages;
@@ -480,12 +514,12 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
       if constexpr (FP8) {
         const float ws = n < N ? wscale[(size_t)n * wscale_stride] : 0.f;
         epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane,
-                                             xscale, ws);
+                                             dir, xscale, ws);
       } else if (GROUPED && xscale != nullptr) {
         epilogue_store_tile<BLOCK_X, EPI, 1>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane,
-                                             xscale, 1.f);
+                                             dir, xscale, 1.f);
       } else {
-        epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane);
+        epilogue_store_tile<BLOCK_X, EPI>(t_addr, &tmap_y, stg, which, n0, m_base, c.split, M, N, out_f32, lane, dir);
       }
       tc_fence_before();
       __syncwarp();
@@ -509,9 +543,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                              const __grid_constant__ CUtensorMap tmap_x,
                              const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
-                             int splits, int n_tiles, int m_tiles, int group_m) {
+                             int splits, int n_tiles, int m_tiles, int group_m, DirectOut dir) {
   gemm_2sm_body<BLOCK_X, EPI, 0>(tmap_w, tmap_x, tmap_y, M, N, K, out_f32, splits, n_tiles, m_tiles,
-                                 group_m, nullptr, nullptr, 0);
+                                 group_m, nullptr, nullptr, 0, dir);
 }
 
 // W8A8 projection of the fp8 checkpoints GPUStack deploys (BASELINE config "Llama-3-70B fp8"):
@@ -525,9 +559,9 @@ gemm_fp8_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                             const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int out_f32,
                             int splits, int n_tiles, int m_tiles, int group_m,
                             const float* __restrict__ xscale, const float* __restrict__ wscale,
-                            int wscale_stride) {
+                            int wscale_stride, DirectOut dir) {
   gemm_2sm_body<BLOCK_X, EPI, 1>(tmap_w, tmap_x, tmap_y, M, N, K, out_f32, splits, n_tiles, m_tiles,
-                                 group_m, xscale, wscale, wscale_stride);
+                                 group_m, xscale, wscale, wscale_stride, dir);
 }
 
 // Grouped (mixture-of-experts) projection: see GroupInfo above.
@@ -538,16 +572,27 @@ gemm_bf16_grouped_2sm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                              const __grid_constant__ CUtensorMap tmap_y, int M, int N, int K, int n_tiles,
                              int m_tiles, int group_m, const float* __restrict__ row_scale,
                              const int32_t* __restrict__ tile_expert,
-                             const int32_t* __restrict__ num_m_tiles) {
+                             const int32_t* __restrict__ num_m_tiles, DirectOut dir) {
   gemm_2sm_body<BLOCK_X, EPI, 0, 1>(tmap_w, tmap_x, tmap_y, M, N, K, 0, 1, n_tiles, m_tiles, group_m,
-                                    row_scale, nullptr, 0, GroupInfo{tile_expert, num_m_tiles});
+                                    row_scale, nullptr, 0, dir, GroupInfo{tile_expert, num_m_tiles});
 }
 
 // Tensor map of the output for the epilogue's TMA stores: [splits][M][N] (bf16, or fp32 when out_f32)
 // or, for the fused SiLU*mul epilogue, the [M][N/2] bf16 activation; box = one warp's chunk.
 template <int BLOCK_X, int EPI>
-static int make_out_tmap(CUtensorMap* ty, void* Y, int M, int N, int64_t ldy, int out_f32, int splits) {
+static int make_out_tmap(CUtensorMap* ty, void* Y, int M, int N, int64_t ldy, int out_f32, int splits,
+                         DirectOut* dir) {
   constexpr int CH = BLOCK_X >= 32 ? 32 : 16;
+  const int es = (EPI == 1 || !out_f32) ? 2 : 4;
+  dir->ptr = nullptr;
+  dir->ldy = ldy;
+  if ((reinterpret_cast<uintptr_t>(Y) & 15) || ((ldy * es) & 15)) {
+    // not describable by a tensor map: the kernel stores element by element; the map passed along is
+    // a placeholder over the (always aligned) first 16 bytes and is never used
+    dir->ptr = Y;
+    return make_tmap_out_3d(ty, reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(Y) & ~(uintptr_t)15), es,
+                            /*cols*/ 8, /*rows*/ 1, /*planes*/ 1, /*ld*/ 8, /*plane*/ 8, /*box*/ 8, 1);
+  }
   if constexpr (EPI == 1)
     return make_tmap_out_3d(ty, Y, 2, (uint64_t)(N / 2), (uint64_t)M, 1, (uint64_t)ldy, 0, 16, CH);
   return make_tmap_out_3d(ty, Y, out_f32 ? 4 : 2, (uint64_t)N, (uint64_t)M, (uint64_t)splits, (uint64_t)ldy,
@@ -579,7 +624,8 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
     attr_set = true;
   }
   CUtensorMap ty;
-  const int rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  DirectOut dir;
+  const int rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits, &dir);
   if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
@@ -590,7 +636,7 @@ static int launch_gemm_mc(const CUtensorMap& tw, const CUtensorMap& tx, void* Y,
   const int clusters = total < max_clusters ? total : max_clusters;
   const int group_m = m_tiles < 8 ? m_tiles : 8;
   cudaError_t e = launch_pdl(kernel, dim3(clusters * MC), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, MC,
-                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m);
+                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m, dir);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -649,7 +695,8 @@ static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, 
   rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
   if (rc) return rc;
   CUtensorMap ty;
-  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  DirectOut dir;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits, &dir);
   if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
@@ -658,7 +705,7 @@ static int launch_gemm_2sm(const void* X, const void* W, void* Y, int M, int N, 
   const int clusters = total < sms / 2 ? total : sms / 2;
   const int group_m = gemm_group_m(m_tiles, K);
   cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
-                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m);
+                             tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m, dir);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_bf16(2sm): launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -688,7 +735,8 @@ static int launch_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, 
   rc = make_tmap_u8_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, 2 * kBlockK);
   if (rc) return rc;
   CUtensorMap ty;
-  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits);
+  DirectOut dir;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, out_f32, splits, &dir);
   if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;
@@ -698,7 +746,7 @@ static int launch_gemm_fp8(const void* X, const void* W, void* Y, int M, int N, 
   const int group_m = gemm_group_m(m_tiles, K / 2);   // a k-block is 128 one-byte elements
   cudaError_t e = launch_pdl(kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2,
                              tw, tx, ty, M, N, K, out_f32, splits, n_tiles, m_tiles, group_m, xscale, wscale,
-                             wscale_stride);
+                             wscale_stride, dir);
   if (e != cudaSuccess) {
     b200_set_error("b200_gemm_fp8: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -897,7 +945,8 @@ static int launch_gemm_grouped(const void* X, const void* W, void* Y, int M, int
   rc = make_tmap_bf16_2d(&tx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BLOCK_X / 2, kBlockK);
   if (rc) return rc;
   CUtensorMap ty;
-  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, 0, 1);
+  DirectOut dir;
+  rc = make_out_tmap<BLOCK_X, EPI>(&ty, Y, M, N, ldy, 0, 1, &dir);
   if (rc) return rc;
   const int n_tiles = (N + kBlockW - 1) / kBlockW;
   const int m_tiles = (M + BLOCK_X - 1) / BLOCK_X;      // capacity; the kernel clamps to the tiles in use
@@ -907,7 +956,7 @@ static int launch_gemm_grouped(const void* X, const void* W, void* Y, int M, int
   const int group_m = gemm_group_m(m_tiles, K);
   cudaError_t e = launch_pdl_cls(kPdlMoe, kernel, dim3(clusters * 2), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes,
                                  stream, 2, tw, tx, ty, M, N, K, n_tiles, m_tiles, group_m, row_scale,
-                                 tile_expert, num_m_tiles);
+                                 tile_expert, num_m_tiles, dir);
   if (e != cudaSuccess) {
     b200_set_error("b200_moe_grouped_gemm: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -56,7 +56,7 @@ SIGNATURES = {
     "b200_paged_attn_decode": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
                                       _i32, _i32, _i32, _f32, _vp]),
     "b200_attn_prefill_tile": (_i32, [_i32, _i32]),
-    "b200_paged_attn_prefill": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp,
+    "b200_paged_attn_prefill": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp,
                                        _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_dev_malloc": (_i32, [_sz, C.POINTER(_vp)]),
     "b200_dev_free": (_i32, [_vp]),

@@ -387,8 +387,8 @@ def paged_attn_prefill(q, q_stride, k_cache, v_cache, block_table, cu_q, ctx_len
     for t, n in ((block_table, "block_table"), (cu_q, "cu_q"), (ctx_lens, "ctx_lens"),
                  (tile_seq, "tile_seq"), (tile_q0, "tile_q0")):
         _req(t, torch.int32, n)
-    check(load().b200_paged_attn_prefill(_p(q), q_stride, _p(k_cache), _p(v_cache), _p(block_table),
-                                         block_table.shape[1], _p(cu_q), _p(ctx_lens), _p(tile_seq),
+    check(load().b200_paged_attn_prefill(_p(q), q_stride, q.shape[0], _p(k_cache), _p(v_cache), k_cache.shape[0],
+                                         _p(block_table), block_table.shape[1], _p(cu_q), _p(ctx_lens), _p(tile_seq),
                                          _p(tile_q0), tile_seq.shape[0], _p(out), Hq, Hkv, D,
                                          k_cache.shape[2], scale, _stream()), "paged_attn_prefill")
     return out

@@ -174,12 +174,14 @@ int b200_paged_attn_decode(const void* q, int64_t q_stride, const void* k_cache,
  * [cu_q[s], cu_q[s+1]) of q; its chunk starts at context position ctx_lens[s] (tokens already in
  * the cache) and attends causally to cache positions [0, ctx_lens[s] + i].  K/V of the chunk must
  * already be in the cache (b200_rope_kv_write runs first).  tile_seq/tile_q0 [num_tiles] list the
- * (sequence, first query offset) of each 32-token query tile, built on the host. */
+ * (sequence, first query offset) of each 32-token query tile, built on the host.  num_tokens = rows
+ * of q, num_blocks = pages of the cache tensors (bounds of the TMA tensor maps of the tcgen05 kernel
+ * that serves head_dim 128 with GQA groups of 4 or 8; other shapes run the mma.sync kernel). */
 /* query-tile size (tokens) the prefill kernel uses for this head grouping: 32 (group <= 4),
  * 16 (group <= 8), 0 = unsupported. */
 int b200_attn_prefill_tile(int Hq, int Hkv);
-int b200_paged_attn_prefill(const void* q, int64_t q_stride, const void* k_cache,
-                            const void* v_cache, const int32_t* block_table, int max_blocks,
+int b200_paged_attn_prefill(const void* q, int64_t q_stride, int num_tokens, const void* k_cache,
+                            const void* v_cache, int num_blocks, const int32_t* block_table, int max_blocks,
                             const int32_t* cu_q, const int32_t* ctx_lens, const int32_t* tile_seq,
                             const int32_t* tile_q0, int num_tiles, void* out, int Hq, int Hkv, int D,
                             int block_size, float scale, void* stream);
