@@ -449,6 +449,35 @@ def micro_rooflines(engine, a, mcfg, pk):
     return res
 
 
+def run_reference_harness(url, a):
+    """One pass of the reference's own load generator (benchmarks/benchmark_serving.py, unmodified:
+    /v1/chat/completions, text prompts, TTFT = first SSE chunk, tok/s = completion tokens / wall)
+    against the server that is up for the e2e leg.  Prompt length is tokenizer dependent (synthetic
+    byte tokenizer here): the achieved mean prompt_tokens is reported."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    try:
+        from run_reference_harness import harness_path
+
+        if harness_path() is None:
+            return {"unavailable": "benchmark_serving.py not present (baseline/_ref/ is filled by __graft_entry__.build())"}
+        cmd = [sys.executable, str(ROOT / "tools" / "run_reference_harness.py"), "-m", "bench-model", "-n", str(a.requests),
+               "-c", str(a.requests), "--max-completion-tokens", str(a.output_len), "--ignore-eos",
+               "--prompt-multiplier", "4", "--request-timeout", "600", "--server-url", url, "--json"]
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(ROOT), timeout=600)
+        if r.returncode != 0 or "{" not in r.stdout:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        d = json.loads(r.stdout[r.stdout.index("{"):])
+        ok = max(1, d.get("successful_requests", 0))
+        return {"script": "benchmarks/benchmark_serving.py (reference, unmodified; tools/run_reference_harness.py)",
+                "endpoint": "/v1/chat/completions", "requests": d.get("total_requests"), "successful": d.get("successful_requests"),
+                "concurrency": d.get("concurrency"), "output_tok_s": d.get("total_completion_tokens_per_second"),
+                "p50_ttft_ms": (d.get("time_to_first_token") or {}).get("p50"),
+                "mean_prompt_tokens": d.get("total_prompt_tokens", 0) / ok,
+                "mean_completion_tokens": d.get("total_completion_tokens", 0) / ok, "seed": 0, "prompt_multiplier": 4}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def run_http_leg(engine, a, mcfg, n_warm, n_timed):
     """Serve the SAME engine over HTTP exactly as `b200-engine serve` does -- this process keeps
     running the engine-core busy loop (on a thread here, bench.py's main thread drives the client),
@@ -481,6 +510,7 @@ def run_http_leg(engine, a, mcfg, n_warm, n_timed):
         r = subprocess.run(cmd + ["--seed", "6000", "--repeat", str(n_timed)], check=True, capture_output=True,
                            text=True, cwd=str(ROOT), timeout=900)
         out = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        harness = run_reference_harness(f"http://127.0.0.1:{port}", a)
     finally:
         front.terminate()
         front.join(timeout=10)
@@ -498,6 +528,7 @@ def run_http_leg(engine, a, mcfg, n_warm, n_timed):
         "successful_requests": sum(o["successful"] for o in out), "requests": sum(o["requests"] for o in out),
         "path": "HTTP /v1/completions SSE: frontend process <-pipe-> engine core; client in a third process "
                 "(host JSON in, host text out)",
+        "harness": harness,
     }
 
 

@@ -66,6 +66,10 @@ SIGNATURES = {
     "b200_allreduce_flag_words": (_i32, [_i32]),
     "b200_allreduce_add_rms_norm": (_i32, [C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _u32, _vp, _vp,
                                            _vp, _vp, _i32, _i32, _f32, _vp]),
+    "b200_allreduce_twoshot_flag_words": (_i32, []),
+    "b200_tp_argmax_select": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b200_allreduce_rs_norm_ag": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _vp, _vp,
+                                         _i32, _i32, _f32, _vp]),
 }
 
 

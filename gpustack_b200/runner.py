@@ -68,11 +68,25 @@ class ModelRunner:
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(ecfg.seed)
         self.oneshot = None
+        self.twoshot = None
         self._ar_toggle = 0
-        if self.tp > 1 and tp_ctx is not None and os.environ.get("B200_TP_ALLREDUCE", "oneshot") == "oneshot":
-            from .tp_comm import OneShotAllReduce
+        self._tp_mode = "nccl"
+        # one-shot moves (tp-1) x the message over NVLink: right for decode-sized messages only
+        self._oneshot_max_bytes = int(os.environ.get("B200_TP_ONESHOT_MAX_BYTES", str(8 << 20)))
+        ar = os.environ.get("B200_TP_ALLREDUCE", "fused")     # fused | oneshot (no two-shot) | nccl
+        if self.tp > 1 and tp_ctx is not None and ar in ("fused", "oneshot"):
+            from .tp_comm import OneShotAllReduce, TwoShotAllReduce
 
             self.oneshot = OneShotAllReduce(tp_ctx, min(512, self.max_tokens), self.H, self.device)
+            if ar == "fused":
+                self.twoshot = TwoShotAllReduce(tp_ctx, self.max_tokens, self.H, self.device)
+                self.xn = self.twoshot.xn          # the peers push normalised rows straight into it
+        self.peer_argmax = None
+        if self.tp > 1 and tp_ctx is not None and os.environ.get("B200_TP_SAMPLER", "peer") == "peer":
+            from .tp_comm import PeerArgmax
+
+            per = (mcfg.vocab_size + self.tp - 1) // self.tp
+            self.peer_argmax = PeerArgmax(tp_ctx, self.max_seqs, per, self.device)
         self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0,
                       "h2d_bytes": 0, "d2h_bytes": 0, "decode_kv_tokens": 0, "prefill_tokens": 0}
         self.launches_per_decode = 0
@@ -169,22 +183,9 @@ class ModelRunner:
                 return ops.gemm(x, w, out=out)
             splitk = True
         if self.tp > 1:
-            ar = self.oneshot
-            # one-shot moves (tp-1) x the message over NVLink: right for decode-sized messages only
-            if ar is not None and T <= ar.max_tokens and T * self.H * 2 * (self.tp - 1) <= (8 << 20):
-                # GEMM writes its partial into a peer-mapped staging buffer; ONE kernel then pulls
-                # every rank's partial over NVLink, sums, adds the residual and normalises.
-                which = self._ar_toggle
-                self._ar_toggle ^= 1
-                mm(ar.stage(which, T))
-                ar.allreduce_add_rms_norm(which, self.resid[:T], norm_w, self.xn[:T], self.resid[:T], T, eps)
-                self.stats["kernel_launches"] += 2
-                return
-            mm(self.hbuf[:T])
-            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
-            ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
-                                   residual_out=self.resid[:T])
-            self.stats["kernel_launches"] += 3
+            mm(self._tp_partial_out(T))
+            self._tp_reduce_norm(T, norm_w)
+            self.stats["kernel_launches"] += 1
             return
         splits = ops.gemm_suggest_splits(T, w.shape[0], w.shape[1]) if (splitk and T <= _SPLITK_MAX_M) else 1
         if splits > 1:
@@ -197,10 +198,49 @@ class ModelRunner:
                                    residual_out=self.resid[:T])
         self.stats["kernel_launches"] += 2
 
+    # ---- tensor parallel: where a row-parallel projection writes its partial sum, and the fused
+    #      (all-reduce + residual add + RMSNorm) that consumes it.  ONE mode per step: the two-shot
+    #      kernel keeps the residual stream sharded by token rows between calls.
+    def _tp_select_mode(self, T: int) -> None:
+        ar = self.oneshot
+        if ar is not None and T <= ar.max_tokens and T * self.H * 2 * (self.tp - 1) <= self._oneshot_max_bytes:
+            self._tp_mode = "oneshot"
+        elif self.twoshot is not None and T <= self.twoshot.max_tokens:
+            self._tp_mode = "twoshot"
+        else:
+            self._tp_mode = "nccl"
+
+    def _tp_partial_out(self, T: int) -> torch.Tensor:
+        if self._tp_mode == "oneshot":
+            return self.oneshot.stage(self._ar_toggle, T)
+        if self._tp_mode == "twoshot":
+            return self.twoshot.stage(T)
+        return self.hbuf[:T]
+
+    def _tp_reduce_norm(self, T: int, norm_w: torch.Tensor) -> None:
+        """xn[:T] = rmsnorm(sum over ranks of the partial + resid) * norm_w; resid updated."""
+        eps = self.mcfg.rms_norm_eps
+        if self._tp_mode == "oneshot":
+            # ONE kernel pulls every rank's partial over NVLink, sums, adds the residual, normalises
+            which = self._ar_toggle
+            self._ar_toggle ^= 1
+            self.oneshot.allreduce_add_rms_norm(which, self.resid[:T], norm_w, self.xn[:T], self.resid[:T], T, eps)
+            self.stats["kernel_launches"] += 1
+        elif self._tp_mode == "twoshot":
+            self.twoshot.rs_norm_ag(self.resid[:T], norm_w, self.resid[:T], T, eps)
+            self.stats["kernel_launches"] += 1
+        else:
+            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
+            ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
+                                   residual_out=self.resid[:T])
+            self.stats["kernel_launches"] += 2
+
     def _layers(self, T: int, attn_fn) -> None:
         """Runs all decoder layers over self.resid[:T] (already holding the embeddings); leaves the
         final-normed hidden states in self.xn[:T]."""
         m, w = self.mcfg, self.w
+        if self.tp > 1:
+            self._tp_select_mode(T)
         pos, slots = self._pos, self._slots
         ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
         self.stats["kernel_launches"] += 2   # embedding (by the caller) + this norm
@@ -239,11 +279,13 @@ class ModelRunner:
         eps = self.mcfg.rms_norm_eps
         ws = self.moe_ws
         ops.gemm(self.xn[:T], lw.router, out=ws.logits[:T])
-        ops.moe_experts(self.xn[:T], ws.logits[:T], lw.w13, lw.w2, self.mcfg.num_experts_per_tok, ws, out=self.hbuf[:T])
         self.stats["kernel_launches"] += 1 + ops.MOE_LAUNCHES
         if self.tp > 1:
-            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
-            self.stats["kernel_launches"] += 1
+            ops.moe_experts(self.xn[:T], ws.logits[:T], lw.w13, lw.w2, self.mcfg.num_experts_per_tok, ws,
+                            out=self._tp_partial_out(T))
+            self._tp_reduce_norm(T, norm_w)
+            return
+        ops.moe_experts(self.xn[:T], ws.logits[:T], lw.w13, lw.w2, self.mcfg.num_experts_per_tok, ws, out=self.hbuf[:T])
         ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T], residual_out=self.resid[:T])
         self.stats["kernel_launches"] += 1
 
@@ -281,6 +323,13 @@ class ModelRunner:
         if self.tp == 1:
             ops.argmax(lg, out_idx=self.out_ids[:n])
             self.stats["kernel_launches"] += 2 + (rows is not None)
+            return
+        if self.peer_argmax is not None:
+            # local (max, argmax) straight into peer-mapped arrays, then ONE kernel picks the global winner
+            pa = self.peer_argmax
+            ops.argmax(lg, out_idx=pa.idxs[:n], out_val=pa.vals[:n])
+            pa.select(self.out_ids, n)
+            self.stats["kernel_launches"] += 3 + (rows is not None)
             return
         ops.argmax(lg, out_idx=self.out_ids[:n], out_val=self.out_vals[:n])
         vals = torch.empty(self.tp, n, dtype=torch.float32, device=self.device)

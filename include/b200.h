@@ -207,6 +207,25 @@ int b200_allreduce_add_rms_norm(void* const* peers_host, void* const* flags_host
                                 int rank, uint32_t epoch, const void* residual, const void* w,
                                 void* y, void* residual_out, int T, int H, float eps, void* stream);
 
+/* Two-shot, sequence-parallel form for large messages (prefill chunks, big decode batches): ONE
+ * kernel = barrier, reduce-scatter by token rows over peer loads, residual add + RMSNorm on this
+ * rank's rows only, all-gather of the normalised rows by peer stores, barrier.
+ * stage_host[r] / xn_host[r] / flags_host[r]: rank r's GEMM-partial staging buffer [T,H] bf16, its
+ * gathered-output buffer [T,H] bf16 (every rank's copy is complete when the kernel ends) and its
+ * flag buffer (b200_allreduce_twoshot_flag_words() zero-initialised uint32 words), as mapped in the
+ * calling process.  The residual stream is sharded by rows between calls: only rows
+ * [rank*ceil(T/world), (rank+1)*ceil(T/world)) of residual / residual_out are read / written. */
+int b200_allreduce_twoshot_flag_words(void);
+/* Greedy sampling over vocabulary-parallel logits: rank r holds, for each of n sequences, the max
+ * (val) and LOCAL argmax (idx) of its lm_head shard in peer-mapped arrays; one CTA per rank reads
+ * every rank's pair over NVLink and writes the global argmax (idx + r * vocab_per_rank; ties -> the
+ * lowest vocabulary index) to out_idx.  flags_host[r]: >= 32 zero-initialised uint32 words. */
+int b200_tp_argmax_select(void* const* val_host, void* const* idx_host, void* const* flags_host,
+                          int world, int rank, int vocab_per_rank, int32_t* out_idx, int n, void* stream);
+int b200_allreduce_rs_norm_ag(void* const* stage_host, void* const* xn_host, void* const* flags_host,
+                              int world, int rank, const void* residual, const void* w,
+                              void* residual_out, int T, int H, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,3 +258,57 @@ def test_bench_client_against_the_frontend_process():
         front.terminate()
         front.join(timeout=10)
         th.join(timeout=10)
+
+
+def test_reference_benchmark_serving_runs_unmodified_against_the_frontend():
+    """BASELINE.json's harness, benchmarks/benchmark_serving.py of the reference, run UNMODIFIED
+    (tools/run_reference_harness.py: runpy + a stand-in for the missing httpx_aiohttp + a seed)
+    against the real frontend process: chat completions, streaming, usage from the last chunk,
+    TTFT on the first chunk -- every request must succeed and the token accounting must add up."""
+    import socket
+    import subprocess
+    import sys
+    import threading
+    import types
+    import urllib.request
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "tools"))
+    from run_reference_harness import harness_path
+
+    if harness_path() is None:
+        pytest.skip("the reference tree is not mounted here (GPU box): no benchmark_serving.py")
+    from gpustack_b200.frontend import spawn_frontend
+
+    eng = StubEngine()
+    eng.sched = Scheduler(2048, 16, 8, 512, 2048, eos_token_id=2)
+    eng.mcfg = types.SimpleNamespace(vocab_size=600, bos_token_id=1, eos_token_id=2)
+    eng.ecfg = types.SimpleNamespace(max_model_len=2048)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    front, core = spawn_frontend(eng, "127.0.0.1", port, "stub-model", None, "error")
+    th = threading.Thread(target=core.run, daemon=True)
+    th.start()
+    try:
+        url = f"http://127.0.0.1:{port}"
+        for _ in range(300):
+            try:
+                if urllib.request.urlopen(url + "/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.1)
+        r = subprocess.run([sys.executable, str(root / "tools" / "run_reference_harness.py"), "-m", "stub-model", "-n", "12",
+                            "-c", "4", "--max-completion-tokens", "16", "--ignore-eos", "--prompt-multiplier", "2",
+                            "--server-url", url, "--json"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res = json.loads(r.stdout[r.stdout.index("{"):])
+        assert res["successful_requests"] == 12 and res["total_requests"] == 12
+        assert res["total_completion_tokens"] == 12 * 16
+        assert res["total_prompt_tokens"] > 12 * 200          # two sample prompts of > 100 bytes each
+        assert res["time_to_first_token"]["p50"] > 0 and res["total_completion_tokens_per_second"] > 0
+    finally:
+        front.terminate()
+        front.join(timeout=10)
+        th.join(timeout=10)

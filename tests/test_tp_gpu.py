@@ -19,14 +19,17 @@ def _port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("allreduce", ["nccl", "oneshot"])
+@pytest.mark.parametrize("allreduce", ["nccl", "oneshot", "twoshot"])
 @pytest.mark.parametrize("eager", ["1", "0"])
 def test_tp_engine_matches_oracle(world, eager, allreduce):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER=eager, B200_TP_ALLREDUCE=allreduce))
+    env = dict(os.environ, TP_EAGER=eager, B200_TP_ALLREDUCE=allreduce)
+    if allreduce == "twoshot":   # every message takes the reduce-scatter / norm-own-rows / all-gather kernel
+        env.update(B200_TP_ALLREDUCE="fused", B200_TP_ONESHOT_MAX_BYTES="0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout
 
@@ -40,6 +43,7 @@ def test_tp2_fp8_and_mixtral_families(family, eager):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, TP_EAGER=eager, TP_FAMILY=family))
+                       env=dict(os.environ, TP_EAGER=eager, TP_FAMILY=family,
+                                B200_TP_ONESHOT_MAX_BYTES=os.environ.get("TP_TEST_ONESHOT_MAX_BYTES", str(8 << 20))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout
