@@ -312,3 +312,81 @@ def test_reference_benchmark_serving_runs_unmodified_against_the_frontend():
         front.terminate()
         front.join(timeout=10)
         th.join(timeout=10)
+
+
+def test_round_robin_relay_alternates_between_two_replicas_and_streams():
+    """tools/rr_relay.py (stand-in for GPUStack's server-side RoundRobinStrategy + worker proxy,
+    gpustack/http_proxy/strategies.py:18-35, routes/worker/proxy.py:26-98): requests alternate over
+    the running instances, SSE streams pass through intact, an unknown model is a 404 envelope."""
+    import socket
+    import subprocess
+    import sys
+    import threading
+    import types
+    import urllib.request
+    from pathlib import Path
+
+    from gpustack_b200.frontend import spawn_frontend
+
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "tools"))
+    from rr_relay import RoundRobin
+
+    rr = RoundRobin()
+    assert [rr.select("m", ["a", "b", "c"]) for _ in range(5)] == ["a", "b", "c", "a", "b"]
+    assert rr.select("m", ["a", "c"]) == "a"             # the instance list changed: a new cycle
+
+    def port():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            return s.getsockname()[1]
+
+    fronts, threads, ports = [], [], []
+    relay = None
+    try:
+        for _ in range(2):
+            eng = StubEngine()
+            eng.mcfg = types.SimpleNamespace(vocab_size=600, bos_token_id=1, eos_token_id=2)
+            eng.ecfg = types.SimpleNamespace(max_model_len=512)
+            p = port()
+            front, core = spawn_frontend(eng, "127.0.0.1", p, "stub-model", None, "error")
+            th = threading.Thread(target=core.run, daemon=True)
+            th.start()
+            fronts.append(front); threads.append(th); ports.append(p)
+        rp = port()
+        relay = subprocess.Popen([sys.executable, str(root / "tools" / "rr_relay.py"), "--port", str(rp), "--model", "stub-model"] +
+                                 [f"http://127.0.0.1:{p}" for p in ports])
+        url = f"http://127.0.0.1:{rp}"
+        for _ in range(300):
+            try:
+                if urllib.request.urlopen(url + "/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.1)
+        for i in range(6):
+            body = json.dumps({"model": "stub-model", "prompt": [5, 6, 7], "max_tokens": 10, "stream": True,
+                               "ignore_eos": True, "stream_options": {"include_usage": True}}).encode()
+            req = urllib.request.Request(url + "/v1/completions", data=body, headers={"content-type": "application/json"})
+            lines = [l.decode().strip() for l in urllib.request.urlopen(req, timeout=30) if l.startswith(b"data: ")]
+            assert lines[-1] == "data: [DONE]"
+            assert json.loads(lines[-2][6:])["usage"]["completion_tokens"] == 10
+        st = json.loads(urllib.request.urlopen(url + "/relay/stats", timeout=5).read())["requests_per_instance"]
+        # 6 generations + the health probes: strictly alternating, so the two counts differ by at most one
+        counts = sorted(st.values())
+        assert counts[1] - counts[0] <= 1 and sum(counts) >= 7
+        bad = urllib.request.Request(url + "/v1/completions", data=json.dumps({"model": "other", "prompt": "x"}).encode(),
+                                     headers={"content-type": "application/json"})
+        try:
+            urllib.request.urlopen(bad, timeout=10)
+            assert False, "expected HTTP 404"
+        except urllib.error.HTTPError as e:
+            assert e.code == 404 and json.loads(e.read())["error"]["code"] == "model_not_found"
+    finally:
+        if relay is not None:
+            relay.terminate()
+            relay.wait(timeout=10)
+        for f in fronts:
+            f.terminate()
+            f.join(timeout=10)
+        for th in threads:
+            th.join(timeout=10)
