@@ -560,6 +560,7 @@ def run_ours(a):
                         max_model_len=min(mcfg.max_position_embeddings, max(1024, a.input_len + a.output_len + 16)),
                         enable_prefix_caching=False,    # every timed token is computed (same as the vLLM baseline run)
                         quantization=a.quantization,
+                        mixed_steps=os.environ.get("B200_MIXED_STEPS", "1") != "0",
                         seed=0)
     t_init = time.perf_counter()
     engine = LLMEngine.from_engine_config(ecfg, mcfg=mcfg)

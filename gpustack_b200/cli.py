@@ -42,6 +42,8 @@ def build_parser() -> argparse.ArgumentParser:
     s.add_argument("--num-gpu-blocks-override", type=int, default=None)
     s.add_argument("--enforce-eager", action="store_true")
     s.add_argument("--enable-prefix-caching", action=argparse.BooleanOptionalAction, default=True)
+    s.add_argument("--mixed-steps", action=argparse.BooleanOptionalAction, default=True,
+                   help="prefill steps also carry one decode token per running sequence (unified token budget)")
     s.add_argument("--seed", type=int, default=0)
     s.add_argument("--quantization", "-q", default=None, choices=[None, "fp8"])
     s.add_argument("--dtype", default="bfloat16")
@@ -75,7 +77,7 @@ def _engine_config(args, tp: int):
                         max_num_batched_tokens=args.max_num_batched_tokens,
                         num_gpu_blocks=args.num_gpu_blocks_override, enforce_eager=args.enforce_eager,
                         enable_prefix_caching=args.enable_prefix_caching, quantization=args.quantization,
-                        seed=args.seed)
+                        mixed_steps=args.mixed_steps, seed=args.seed)
 
 
 def make_engine(ecfg):

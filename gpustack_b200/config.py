@@ -255,6 +255,7 @@ class EngineConfig:
     enforce_eager: bool = False               # skip CUDA-graph capture of decode steps
     enable_prefix_caching: bool = True        # reuse full KV blocks across requests (reference engine default)
     quantization: Optional[str] = None        # None | "fp8" (W8A8: online per-tensor weights, per-token activations)
+    mixed_steps: bool = True                  # prefill steps also carry the running sequences' decode tokens
     seed: int = 0
     block_size: int = 16
     cuda_graph_sizes: list = field(default_factory=list)

@@ -117,7 +117,10 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
+    // The whole warp walks the block table (lane l holds the page id of page base + l, one coalesced
+    // load per 32 pages = 8 KV blocks; a dependent global load per TMA would serialise the ring at
+    // L2 latency); lane 0 waits for the slot and issues the copies.
+    if (lane == 0) {
       mbar_expect_tx(q_full, kFaQBytes);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -126,28 +129,38 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tma_load_2d(smem + h * kFaQHalfBytes + g * TPT * 128, &tmap_q, q_full, (kvh * G + g) * kFaD + h * 64,
                       q_begin + q0, kEvictFirst);
       }
-      const int32_t* bt = block_table + (size_t)seq * max_blocks;
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_blocks; ++j) {
+    }
+    const int32_t* bt = block_table + (size_t)seq * max_blocks;
+    constexpr int PPB = kFaKv / kFaPage;   // pages per KV block
+    int slot = 0;
+    uint32_t phase = 0;
+    int my_blk = 0;
+    for (int j = 0; j < n_blocks; ++j) {
+      if ((j & 7) == 0) {   // refill: pages [j*4, j*4 + 32)
+        const int page = j * PPB + lane;
+        my_blk = page < n_pages_seq ? __ldg(bt + page) : 0;   // block 0: the all-zero null block
+      }
+      int rows[PPB];
+#pragma unroll
+      for (int p = 0; p < PPB; ++p)
+        rows[p] = (__shfl_sync(0xffffffffu, my_blk, ((j & 7) * PPB + p)) * Hkv + kvh) * kFaPage;
+      if (lane == 0) {
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv) {   // K_j then V_j
           mbar_wait_guarded(&kv_empty[slot], phase ^ 1);
           mbar_expect_tx(&kv_full[slot], kFaSlotBytes);
           uint8_t* dst = smem + kFaOffKV + slot * kFaSlotBytes;
 #pragma unroll
-          for (int p = 0; p < kFaKv / kFaPage; ++p) {
-            const int page = j * (kFaKv / kFaPage) + p;
-            const int blk = page < n_pages_seq ? bt[page] : 0;   // block 0: the all-zero null block
-            const int row = (blk * Hkv + kvh) * kFaPage;
+          for (int p = 0; p < PPB; ++p) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               tma_load_2d(dst + h * kFaHalfBytes + p * (kFaPage * 128), kv ? &tmap_v : &tmap_k, &kv_full[slot],
-                          h * 64, row, kEvictNormal);
+                          h * 64, rows[p], kEvictNormal);
           }
           if (++slot == kFaSlots) { slot = 0; phase ^= 1; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer

@@ -19,13 +19,13 @@ import torch
 from .config import EngineConfig, ModelConfig
 from .lib import B200Error
 from .runner import ModelRunner
-from .scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
+from .scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
 from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, random_state_dict,
                       shard_state_dict)
 
 log = logging.getLogger("b200.engine")
 
-_KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED, _KIND_GATHER = 0, 1, 2, 3, 4, 5
+_KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED, _KIND_GATHER, _KIND_MIXED = 0, 1, 2, 3, 4, 5, 6
 
 
 class ShmStepChannel:
@@ -201,7 +201,8 @@ class LLMEngine:
         self.runner.init_kv_cache(n)
         self.runner.capture_graphs()
         self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
-                               ecfg.max_model_len, mcfg.eos_token_ids or mcfg.eos_token_id, ecfg.enable_prefix_caching)
+                               ecfg.max_model_len, mcfg.eos_token_ids or mcfg.eos_token_id, ecfg.enable_prefix_caching,
+                               mixed_steps=ecfg.mixed_steps)
         self.requests: Dict[str, Request] = {}
         self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
         self.step_time = {"prefill": 0.0, "decode": 0.0}
@@ -281,13 +282,23 @@ class LLMEngine:
             out = s.update_decode(plan, toks)
             self.step_time["decode"] += time.perf_counter() - t0
         else:
-            chunks = [r.all_ids[st:st + n] for r, st, n in zip(plan.reqs, plan.starts, plan.lens)]
-            tables = [r.blocks for r in plan.reqs]
+            mixed = isinstance(plan, MixedPlan)
+            pre = plan.prefill if mixed else plan
+            s = self.sched
+            B = plan.batch if mixed else 0
+            dec = (B, s.last_token, s.num_computed, s.block_table) if mixed else None
+            chunks = [r.all_ids[st:st + n] for r, st, n in zip(pre.reqs, pre.starts, pre.lens)]
+            tables = [r.blocks for r in pre.reqs]
             if self.tp:
-                self._bcast_prefill(chunks, plan.starts, tables, plan.sample)
-            toks = self.runner.prefill(chunks, plan.starts, tables, plan.sample)
-            toks = self._apply_sampling([r for r, smp in zip(plan.reqs, plan.sample) if smp], toks)
-            out = self.sched.update_prefill(plan, toks)
+                self._bcast_prefill(chunks, pre.starts, tables, pre.sample, dec)
+            toks = self.runner.prefill(chunks, pre.starts, tables, pre.sample, decode=dec)
+            sampled = [r for r, smp in zip(pre.reqs, pre.sample) if smp]
+            toks = self._apply_sampling(sampled + list(s.rows[:B]), toks)
+            ns = len(sampled)
+            if mixed:
+                out = s.update_mixed(plan, toks[:ns], np.asarray(toks[ns:ns + B], dtype=np.int32))
+            else:
+                out = s.update_prefill(pre, toks)
             self.step_time["prefill"] += time.perf_counter() - t0
         self.counters["steps"] += 1
         self.counters["generation_tokens"] += len(out.token_ids)
@@ -317,14 +328,18 @@ class LLMEngine:
         toks[rows] = sampled
         return toks
 
-    def _bcast_prefill(self, chunks, starts, tables, sample) -> None:
+    def _bcast_prefill(self, chunks, starts, tables, sample, dec=None) -> None:
         S = len(chunks)
         lens = [len(c) for c in chunks]
         nb = [len(t) for t in tables]
-        flat = np.concatenate([np.asarray(lens), np.asarray(starts), np.asarray(sample, dtype=np.int32),
-                               np.asarray(nb)] + [np.asarray(t) for t in tables] +
-                              [np.asarray(c) for c in chunks]).astype(np.int32)
-        self.tp.bcast_step([_KIND_PREFILL, S], flat)
+        parts = [np.asarray(lens), np.asarray(starts), np.asarray(sample, dtype=np.int32), np.asarray(nb)] + \
+            [np.asarray(t) for t in tables] + [np.asarray(c) for c in chunks]
+        B = 0
+        if dec is not None:     # mixed step: the decode rows' (last token, position, block table) follow
+            B, last, comp, bt = dec
+            parts += [last[:B], comp[:B], bt[:B].reshape(-1)]
+        flat = np.concatenate([np.asarray(p).reshape(-1) for p in parts]).astype(np.int32)
+        self.tp.bcast_step([_KIND_MIXED if dec is not None else _KIND_PREFILL, S, B], flat)
 
     def shutdown(self) -> None:
         if self.tp and self.tp.rank == 0:
@@ -414,4 +429,8 @@ class TPWorker:
                 chunks = []
                 for s in range(S):
                     chunks.append(p[off:off + lens[s]]); off += lens[s]
-                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample])
+                dec = None
+                if kind == _KIND_MIXED:
+                    B = h[2]
+                    dec = (B, p[off:off + B], p[off + B:off + 2 * B], p[off + 2 * B:off + 2 * B + B * mb].reshape(B, mb))
+                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample], decode=dec)

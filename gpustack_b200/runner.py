@@ -118,7 +118,7 @@ class ModelRunner:
         self.cos_sin = self._cos_sin_cache().to(dev)
         # one int32 staging area for all step inputs (host pinned + device mirror)
         n_tiles_max = T // self.prefill_tile + self.max_seqs + 1
-        self.stage_words = _align(3 * T) + 4 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
+        self.stage_words = _align(3 * T) + 5 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
             + self.max_seqs * self.max_blocks + 64
         self.stage_host = torch.zeros(self.stage_words, dtype=torch.int32, pin_memory=True)
         self.stage_np = self.stage_host.numpy()
@@ -128,7 +128,7 @@ class ModelRunner:
         S = self.max_seqs
         self.d_ids, self.d_pos, self.d_slots, self.d_lens = 0, S, 2 * S, 3 * S
         self.d_bt = 4 * S
-        self.attn_ws: Dict[int, torch.Tensor] = {}
+        self._attn_ws: Optional[torch.Tensor] = None
 
     def _cos_sin_cache(self) -> torch.Tensor:
         # $VLLM/model_executor/layers/rotary_embedding/base.py:71-93; kept in the model dtype
@@ -136,6 +136,21 @@ class ModelRunner:
         t = torch.arange(self.max_model_len, dtype=torch.float)
         freqs = torch.einsum("i,j -> ij", t, inv_freq)
         return torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(BF16)
+
+    def _decode_attn_plan(self, B: int):
+        """(KV splits, workspace) of the split-KV decode attention for a batch of B sequences.  ONE
+        workspace, sized for the worst batch, serves every batch size (eager, mixed and graph steps
+        never overlap on the stream)."""
+        splits = ops.attn_decode_splits(B, self.Hkv, self.max_model_len)
+        if self._attn_ws is None:
+            from .lib import load
+
+            L = load()
+            need = max(L.b200_attn_decode_workspace_bytes(b, self.Hq, self.D,
+                                                          ops.attn_decode_splits(b, self.Hkv, self.max_model_len))
+                       for b in range(1, self.max_seqs + 1))
+            self._attn_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        return splits, self._attn_ws
 
     def kv_block_bytes(self) -> int:
         return 2 * self.mcfg.num_hidden_layers * self.Hkv * self.block_size * self.D * 2
@@ -349,10 +364,7 @@ class ModelRunner:
         lens = sd[self.d_lens:self.d_lens + B]
         bt = sd[self.d_bt:self.d_bt + B * self.max_blocks].view(B, self.max_blocks)
         ops.embedding(ids, self.w.embed, out=self.resid[:B])
-        splits = ops.attn_decode_splits(B, self.Hkv, self.max_model_len)
-        ws = self.attn_ws.get(B)
-        if ws is None:
-            ws = self.attn_ws[B] = ops.attn_decode_workspace(B, self.Hq, self.D, splits, self.device)
+        splits, ws = self._decode_attn_plan(B)
 
         def attn(l):
             ops.paged_attn_decode(self.qkv[:B], self.qkv_width, self.k_cache[l], self.v_cache[l], bt, lens,
@@ -427,15 +439,21 @@ class ModelRunner:
 
     # ------------------------------------------------------------------------------ prefill
     def prefill(self, token_chunks: Sequence[Sequence[int]], starts: Sequence[int], block_tables: Sequence[Sequence[int]],
-                sample: Sequence[bool]) -> np.ndarray:
+                sample: Sequence[bool], decode=None) -> np.ndarray:
         """Runs one (chunked) prefill step.  token_chunks[s] are the ids of chunk s, which occupies
         positions [starts[s], starts[s]+len).  Returns the greedy token of every chunk with
-        sample[s] == True, in order."""
+        sample[s] == True, in order.
+        decode = (B, last_token, num_computed, block_table) makes it a MIXED step: rows 0..B-1 of the
+        scheduler's persistent batch ride along with one decode token each (appended after the
+        prefill tokens: same GEMMs / norms / RoPE launches, the weights are streamed once for
+        both); their B tokens follow the prefill tokens in the returned array."""
         S = len(token_chunks)
         lens = [len(c) for c in token_chunks]
-        T = sum(lens)
-        if T > self.max_tokens or S > self.max_seqs:
-            raise B200Error(f"prefill step too large: {T} tokens / {S} sequences")
+        Tp = sum(lens)
+        Bd = 0 if decode is None else int(decode[0])
+        T = Tp + Bd
+        if T > self.max_tokens or S + Bd > self.max_seqs:
+            raise B200Error(f"prefill step too large: {T} tokens / {S + Bd} sequences")
         bs = self.block_size
         st = self.stage_np
         o_ids, o_pos, o_slots = 0, _align(T), 2 * _align(T)
@@ -444,13 +462,16 @@ class ModelRunner:
         o_rows = o_ctx + _align(S)
         tile_seq, tile_q0 = ops.build_prefill_tiles(lens, self.prefill_tile, starts)
         nt = len(tile_seq)
-        o_ts = o_rows + _align(S)
+        o_ts = o_rows + _align(S + Bd)
         o_tq = o_ts + _align(nt)
-        o_bt = o_tq + _align(nt)
-        end = o_bt + S * self.max_blocks
+        o_dl = o_tq + _align(nt)              # decode rows: sequence lengths
+        o_bt = o_dl + _align(Bd)
+        end = o_bt + (S + Bd) * self.max_blocks
+        if end > self.stage_words:
+            raise B200Error("step inputs exceed the staging buffer")
         cu = np.zeros(S + 1, dtype=np.int32)
         np.cumsum(lens, out=cu[1:])
-        bt = np.zeros((S, self.max_blocks), dtype=np.int32)
+        bt = np.zeros((S + Bd, self.max_blocks), dtype=np.int32)
         for s in range(S):
             a, b = cu[s], cu[s + 1]
             tbl = np.asarray(block_tables[s], dtype=np.int32)
@@ -462,6 +483,16 @@ class ModelRunner:
         st[o_cu:o_cu + S + 1] = cu
         st[o_ctx:o_ctx + S] = starts
         sample_rows = [int(cu[s + 1]) - 1 for s in range(S) if sample[s]]
+        if Bd:
+            _, last_token, num_computed, dbt = decode
+            dpos = np.asarray(num_computed[:Bd], dtype=np.int32)
+            st[o_ids + Tp:o_ids + T] = last_token[:Bd]
+            st[o_pos + Tp:o_pos + T] = dpos
+            st[o_slots + Tp:o_slots + T] = dbt[np.arange(Bd), dpos // bs] * bs + dpos % bs
+            st[o_dl:o_dl + Bd] = dpos + 1
+            bt[S:] = dbt[:Bd]
+            sample_rows += list(range(Tp, T))
+            self.stats["decode_kv_tokens"] += int(dpos.sum()) + Bd
         ns = len(sample_rows)
         st[o_rows:o_rows + ns] = sample_rows
         st[o_ts:o_ts + nt] = tile_seq
@@ -473,18 +504,30 @@ class ModelRunner:
         self._pos, self._slots = sd[o_pos:o_pos + T], sd[o_slots:o_slots + T]
         cu_d, ctx_d = sd[o_cu:o_cu + S + 1], sd[o_ctx:o_ctx + S]
         ts_d, tq_d = sd[o_ts:o_ts + nt], sd[o_tq:o_tq + nt]
-        bt_d = sd[o_bt:end].view(S, self.max_blocks)
+        bt_all = sd[o_bt:end].view(S + Bd, self.max_blocks)
+        bt_d = bt_all[:S]
         ops.embedding(ids, self.w.embed, out=self.resid[:T])
+        if Bd:
+            dl_d, dbt_d = sd[o_dl:o_dl + Bd], bt_all[S:]
+            splits, ws = self._decode_attn_plan(Bd)
 
         def attn(l):
-            ops.paged_attn_prefill(self.qkv[:T], self.qkv_width, self.k_cache[l], self.v_cache[l], bt_d, cu_d,
-                                   ctx_d, ts_d, tq_d, self.attn_out[:T], self.Hq, self.Hkv, self.D, self.scale)
+            # the prefill kernel only ever touches the first Tp rows (q is read through cu_q / tiles)
+            if nt:
+                ops.paged_attn_prefill(self.qkv[:Tp], self.qkv_width, self.k_cache[l], self.v_cache[l], bt_d, cu_d,
+                                       ctx_d, ts_d, tq_d, self.attn_out[:Tp], self.Hq, self.Hkv, self.D, self.scale)
+            if Bd:   # the riding decode rows: one query token each, the split-KV decode kernel
+                ops.paged_attn_decode(self.qkv[Tp:T], self.qkv_width, self.k_cache[l], self.v_cache[l], dbt_d, dl_d,
+                                      self.attn_out[Tp:T], self.Hq, self.Hkv, self.D, self.scale,
+                                      num_splits=splits, workspace=ws)
+                self.stats["kernel_launches"] += 1 + (splits > 1)
 
         self._layers(T, attn)
         self.stats["prefill_steps"] += 1
+        self.stats["mixed_steps"] = self.stats.get("mixed_steps", 0) + (1 if Bd else 0)
         self.stats["h2d_bytes"] += end * 4
         self.stats["d2h_bytes"] += ns * 4
-        self.stats["prefill_tokens"] += T
+        self.stats["prefill_tokens"] += Tp
         if ns == 0:
             torch.cuda.current_stream().synchronize()
             return np.zeros(0, dtype=np.int32)

@@ -1,9 +1,12 @@
 """Continuous-batching scheduler (host side).
 
 Counterpart of the reference engine's Scheduler.schedule ($VLLM/v1/core/sched/scheduler.py:329):
-token-budgeted prefill batches (with chunking of long prompts), decode batches over every running
-sequence, block allocation / prefix-cache reuse / preemption through the BlockPool.  Policy: prefill-first (best
-TTFT and throughput for the benchmark_serving.py workload), decode otherwise.
+token-budgeted steps: the running sequences' decode tokens first, the rest of the budget for prefill
+chunks of admitted / waiting prompts (with chunking of long prompts) -- ONE mixed step serves both, so
+running requests keep producing a token per step while new prompts are prefilled (the reference
+scheduler's unified token budget).  Steps without prompts to prefill are pure decode steps (CUDA-graph
+path); block allocation / prefix-cache reuse / preemption go through the BlockPool.
+`mixed_steps=False` restores the round-1 policy (prefill steps never carry decode tokens).
 
 Running sequences live in a compact "persistent batch" of numpy arrays (rows 0..B-1) so that a
 decode step's inputs are produced by a handful of vectorised numpy ops instead of per-request
@@ -76,6 +79,17 @@ class DecodePlan:
 
 
 @dataclass
+class MixedPlan:
+    """One step = prefill chunks + one decode token for rows 0..batch-1 of the persistent batch."""
+    prefill: PrefillPlan
+    batch: int
+
+    @property
+    def num_tokens(self) -> int:
+        return self.prefill.num_tokens + self.batch
+
+
+@dataclass
 class StepOutput:
     req_ids: List[str]
     token_ids: List[int]
@@ -84,12 +98,13 @@ class StepOutput:
 
 class Scheduler:
     def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: int, eos_token_id, enable_prefix_caching: bool = False):
+                 max_model_len: int, eos_token_id, enable_prefix_caching: bool = False, mixed_steps: bool = True):
         """eos_token_id: one id, an iterable of ids (every turn terminator of the checkpoint), or None."""
         self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching)
         self.block_size = block_size
         self.max_num_seqs = max_num_seqs
         self.max_tokens_per_step = max_num_batched_tokens
+        self.mixed_steps = mixed_steps
         self.max_model_len = max_model_len
         if eos_token_id is None:
             eos_ids = []
@@ -178,9 +193,14 @@ class Scheduler:
             r.blocks = []
 
     def schedule(self):
-        """Returns a PrefillPlan, a DecodePlan, or None when idle."""
-        plan = self._schedule_prefill()
+        """Returns a PrefillPlan, a MixedPlan, a DecodePlan, or None when idle."""
+        ride = len(self.rows) if self.mixed_steps else 0     # decode tokens come out of the same budget
+        plan = self._schedule_prefill(self.max_tokens_per_step - ride) if ride < self.max_tokens_per_step else None
         if plan is not None:
+            if ride:
+                self._ensure_decode_blocks()                 # may preempt rows (never the ones being prefilled)
+                if self.rows:
+                    return MixedPlan(plan, len(self.rows))
             return plan
         if self.rows:
             self._ensure_decode_blocks()
@@ -188,8 +208,9 @@ class Scheduler:
                 return DecodePlan(batch=len(self.rows))
         return None
 
-    def _schedule_prefill(self) -> Optional[PrefillPlan]:
-        budget = self.max_tokens_per_step
+    def _schedule_prefill(self, budget: Optional[int] = None) -> Optional[PrefillPlan]:
+        if budget is None:
+            budget = self.max_tokens_per_step
         reqs, starts, lens, sample = [], [], [], []
         # 1. continue partially prefilled prompts
         for r in self.prefilling:
@@ -323,6 +344,13 @@ class Scheduler:
             else:
                 self._install_row(r, tok)
         return out
+
+    def update_mixed(self, plan: MixedPlan, sampled_prefill: Sequence[int], sampled_decode: np.ndarray) -> StepOutput:
+        """Decode rows first (their eviction swaps only touch rows < batch), then the prefill chunks
+        (completed prompts are installed as new rows at the end)."""
+        out = self.update_decode(DecodePlan(plan.batch), sampled_decode)
+        pre = self.update_prefill(plan.prefill, sampled_prefill)
+        return StepOutput(out.req_ids + pre.req_ids, out.token_ids + pre.token_ids, out.finished + pre.finished)
 
     def update_decode(self, plan: DecodePlan, sampled: np.ndarray) -> StepOutput:
         B = plan.batch

@@ -33,6 +33,24 @@ def _engine(cfg_o, seed=7, **kw):
     return eng, O.OracleLlama(cfg_o, weights, quantization=ecfg.quantization)
 
 
+def _assert_greedy_matches_oracle(oracle, prompts, outs, tol_rel=2e-2, min_checked=None):
+    """Margin rule used everywhere: the oracle is teacher-forced on the ENGINE's tokens; wherever its
+    top-2 margin exceeds the stated tolerance the engine's token must be the oracle's argmax.  A token
+    that an indexing / chunk-boundary bug flips fails here even if 90 % of the sequence still agrees."""
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        oracle.reset()
+        logits = oracle.forward(i, p)[-1]
+        n_checked = 0
+        for t in range(len(o)):
+            top2 = torch.topk(logits, 2).values
+            margin = float(top2[0] - top2[1])
+            if margin > tol_rel * float(logits.abs().max()):
+                assert int(torch.argmax(logits)) == o[t], f"seq {i} step {t}: margin {margin}"
+                n_checked += 1
+            logits = oracle.forward(i, [o[t]])[-1]
+        assert n_checked >= (len(o) // 3 if min_checked is None else min_checked), (i, n_checked)
+
+
 @pytest.mark.parametrize("cfg_o", [O.TINY, O.TINY128, O.TINY_QWEN2, O.TINY_MIXTRAL],
                          ids=["tiny64", "tiny128", "qwen2-bias-tied-g7", "mixtral-8x-top2"])
 @pytest.mark.parametrize("eager", [True, False], ids=["eager", "graphs"])
@@ -83,15 +101,40 @@ def test_chunked_prefill_and_preemption_match_unchunked():
     eng_a, _ = _engine(O.TINY, mbt=512, blocks=256, enforce_eager=True)
     ref = eng_a.generate(prompts, sp)
     del eng_a
-    eng_b, _ = _engine(O.TINY, mbt=64, blocks=50, enforce_eager=True, max_num_seqs=4)
+    eng_b, oracle = _engine(O.TINY, mbt=64, blocks=50, enforce_eager=True, max_num_seqs=4)
     got = eng_b.generate(prompts, sp)
-    assert eng_b.runner.stats["prefill_steps"] > 4
-    # chunking changes the reduction order inside attention only marginally; tokens must agree
-    # except at near-ties, so require >= 90% positional agreement and identical first tokens
+    assert eng_b.runner.stats["prefill_steps"] > 4 and eng_b.sched.num_preemptions > 0
+    # chunking / recomputation change the reduction order marginally: both runs must match the
+    # oracle wherever its margin exceeds the tolerance (not merely "90 % of the tokens")
+    _assert_greedy_matches_oracle(oracle, prompts, ref)
+    _assert_greedy_matches_oracle(oracle, prompts, got)
     for a, b in zip(ref, got):
         assert a[0] == b[0]
-        agree = sum(x == y for x, y in zip(a, b)) / len(a)
-        assert agree >= 0.9 or a[: len(a) // 2] == b[: len(b) // 2]
+
+
+def test_mixed_prefill_decode_steps_match_the_oracle():
+    """Requests arrive while others are decoding: their prompts are prefilled (in chunks) by MIXED
+    steps that also carry one decode token per running sequence (decode rows ride behind the
+    prefill tokens: same GEMM / norm / RoPE launches, split-KV decode attention for the riders)."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    g = torch.Generator().manual_seed(17)
+    prompts = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (60, 33, 150, 9, 97)]
+    sp = SamplingParams(max_tokens=18, ignore_eos=True)
+    for eager in (True, False):
+        eng, oracle = _engine(O.TINY, mbt=64, blocks=128, enforce_eager=eager, max_num_seqs=8, cuda_graph_sizes=[1, 2, 4, 8])
+        reqs = []
+        for i, p in enumerate(prompts):          # one new arrival every second engine step
+            eng.add_request(f"m{i}", p, sp)
+            reqs.append(eng.requests[f"m{i}"])
+            eng.step(); eng.step()
+        while eng.has_work():
+            eng.step()
+        assert eng.runner.stats["mixed_steps"] >= 4
+        _assert_greedy_matches_oracle(oracle, prompts, [r.output_ids for r in reqs])
+        assert all(len(r.output_ids) == 18 for r in reqs)
+        assert eng.sched.pool.num_free == eng.sched.pool.num_total
+        del eng
 
 
 def test_eos_and_stop_handling():
@@ -139,17 +182,17 @@ def test_prefix_caching_matches_uncached_run():
     ref = [eng_off.generate([p], sp)[0] for p in prompts]
     ref_turn2 = eng_off.generate([prompts[0] + ref[0] + [5, 6, 7]], sp)[0]
     del eng_off
-    eng, _ = _engine(O.TINY, enforce_eager=True, enable_prefix_caching=True)
+    eng, oracle = _engine(O.TINY, enforce_eager=True, enable_prefix_caching=True)
     got = [eng.generate([prompts[0]], sp)[0]]
     assert eng.sched.pool.hits == 0
     got += eng.generate(prompts[1:], sp)                    # three requests, all hit the 5 head blocks
     assert eng.sched.pool.hits == 3 * 80
     got_turn2 = eng.generate([prompts[0] + got[0] + [5, 6, 7]], sp)[0]
     assert eng.sched.pool.hits >= 3 * 80 + 96               # prompt + generated tokens of turn 1
+    all_prompts = prompts + [prompts[0] + got[0] + [5, 6, 7]]
+    _assert_greedy_matches_oracle(oracle, all_prompts, got + [got_turn2])      # cached blocks hold the right K/V
     for a, b in zip(ref + [ref_turn2], got + [got_turn2]):
         assert a[0] == b[0]
-        agree = sum(x == y for x, y in zip(a, b)) / len(a)
-        assert agree >= 0.9 or a[: len(a) // 2] == b[: len(b) // 2]
     assert eng.sched.pool.num_free == eng.sched.pool.num_total
 
 

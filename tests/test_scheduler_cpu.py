@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from gpustack_b200.kv_cache import BlockPool, KVCacheManager
-from gpustack_b200.scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler
+from gpustack_b200.scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler
 
 
 def mk(num_blocks=64, max_seqs=8, budget=64, max_len=256, eos=2):
@@ -16,6 +16,8 @@ def req(i, n, **kw):
 
 
 def drive(s, plan, tok=7):
+    if isinstance(plan, MixedPlan):
+        return s.update_mixed(plan, [tok] * sum(plan.prefill.sample), np.full(plan.batch, tok, dtype=np.int32))
     if isinstance(plan, PrefillPlan):
         return s.update_prefill(plan, [tok] * sum(plan.sample))
     return s.update_decode(plan, np.full(plan.batch, tok, dtype=np.int32))
@@ -54,6 +56,35 @@ def test_prefill_first_then_decode_until_length():
     assert out.req_ids == ["r0"] and out.finished == ["length"]
     assert s.schedule() is None and not s.has_work()
     assert s.pool.num_free == s.pool.num_total
+
+
+def test_mixed_steps_carry_decode_tokens_with_the_prefill_chunks():
+    """A prompt that arrives while another request is decoding is prefilled in a MIXED step: the
+    running row produces its token in the same step, the decode token is charged to the budget."""
+    s = mk(budget=32)
+    s.add(req(0, 10, max_tokens=5, ignore_eos=True))
+    out = drive(s, s.schedule())
+    assert out.req_ids == ["r0"]
+    s.add(req(1, 40, max_tokens=3, ignore_eos=True))
+    p = s.schedule()
+    assert isinstance(p, MixedPlan) and p.batch == 1
+    assert p.prefill.lens == [31] and p.prefill.sample == [False] and p.num_tokens == 32   # 32 - 1 decode token
+    out = drive(s, p, tok=9)
+    assert out.req_ids == ["r0"] and out.token_ids == [9] and s.num_computed[0] == 11
+    p = s.schedule()
+    assert isinstance(p, MixedPlan) and p.prefill.lens == [9] and p.prefill.sample == [True]
+    out = drive(s, p, tok=8)
+    assert out.req_ids == ["r0", "r1"] and out.finished == [None, None]
+    assert [r.req_id for r in s.rows] == ["r0", "r1"] and s.num_computed[:2].tolist() == [12, 40]
+    d = s.schedule()
+    assert isinstance(d, DecodePlan) and d.batch == 2            # nothing left to prefill: pure decode step
+    # the round-1 policy is still available
+    s2 = Scheduler(64, 16, 8, 32, 256, 2, mixed_steps=False)
+    s2.add(req(0, 10, max_tokens=5, ignore_eos=True))
+    drive(s2, s2.schedule())
+    s2.add(req(1, 40, max_tokens=3, ignore_eos=True))
+    p2 = s2.schedule()
+    assert isinstance(p2, PrefillPlan) and p2.lens == [32]
 
 
 def test_chunked_prefill_respects_token_budget():
@@ -360,7 +391,7 @@ def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budg
     BS, max_len = 16, 160
     s = Scheduler(num_blocks, BS, max_seqs, budget, max_len, 2, enable_prefix_caching=caching)
     heads = [rng.randint(3, 300, size=n).tolist() for n in (16, 40)]
-    live, nreq, steps, finished = {}, 0, 0, 0
+    live, nreq, steps, finished, mixed_seen = {}, 0, 0, 0, 0
     while steps < 600:
         steps += 1
         if nreq < 25 and rng.rand() < 0.4:
@@ -383,19 +414,20 @@ def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budg
             if nreq >= 25 and not s.has_work():
                 break
             continue
-        if isinstance(plan, PrefillPlan):
-            assert 0 < plan.num_tokens <= budget and len(plan.reqs) == len(set(id(r) for r in plan.reqs))
+        pre = plan.prefill if isinstance(plan, MixedPlan) else plan if isinstance(plan, PrefillPlan) else None
+        B = 0 if isinstance(plan, PrefillPlan) else plan.batch
+        if pre is not None:
+            assert 0 < pre.num_tokens and pre.num_tokens + B <= budget      # decode tokens share the budget
+            assert len(pre.reqs) == len(set(id(r) for r in pre.reqs))
             assert len(s.rows) + len(s.prefilling) <= max_seqs
-            for r, st_, n, smp in zip(plan.reqs, plan.starts, plan.lens, plan.sample):
+            assert not any(r in s.rows for r in pre.reqs)
+            for r, st_, n, smp in zip(pre.reqs, pre.starts, pre.lens, pre.sample):
                 assert n > 0 and st_ == r.num_computed and st_ + n <= r.prefill_target
                 assert smp == (st_ + n == r.prefill_target)
                 assert len(r.blocks) * BS >= r.prefill_target + 1            # room for the first decode slot
-                if caching and st_ > 0 and r in plan.reqs and st_ % BS == 0 and r.num_cached_tokens:
+                if caching and st_ > 0 and st_ % BS == 0 and r.num_cached_tokens:
                     assert r.num_cached_tokens <= r.prefill_target - 1
-            toks = rng.choice([2, 7, 9], size=sum(plan.sample), p=[0.1, 0.45, 0.45]).tolist()
-            out = s.update_prefill(plan, toks)
-        else:
-            B = plan.batch
+        if B:
             assert 0 < B <= max_seqs and B == len(s.rows)
             for i, r in enumerate(s.rows):
                 assert r.row == i and int(s.n_blocks[i]) == len(r.blocks)
@@ -403,7 +435,15 @@ def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budg
                 pos = int(s.num_computed[i])
                 assert pos // BS < len(r.blocks) and pos == len(r.prompt_ids) + len(r.output_ids) - 1
                 assert int(s.last_token[i]) == r.all_ids[-1]
-            out = s.update_decode(plan, rng.choice([2, 7, 9], size=B, p=[0.1, 0.45, 0.45]).astype(np.int32))
+        ptoks = rng.choice([2, 7, 9], size=sum(pre.sample), p=[0.1, 0.45, 0.45]).tolist() if pre is not None else []
+        dtoks = rng.choice([2, 7, 9], size=B, p=[0.1, 0.45, 0.45]).astype(np.int32)
+        if isinstance(plan, MixedPlan):
+            mixed_seen += 1
+            out = s.update_mixed(plan, ptoks, dtoks)
+        elif pre is not None:
+            out = s.update_prefill(plan, ptoks)
+        else:
+            out = s.update_decode(plan, dtoks)
         finished += sum(f is not None for f in out.finished)
         # ownership: a block has several owners only if it is a cached full block inside every owner's computed prefix
         owners = {}

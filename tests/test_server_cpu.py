@@ -12,7 +12,7 @@ from openai.types.chat import ChatCompletion, ChatCompletionChunk
 from openai.types.completion import Completion
 
 from gpustack_b200.async_engine import AsyncEngine
-from gpustack_b200.scheduler import DecodePlan, PrefillPlan, Request, SamplingParams, Scheduler
+from gpustack_b200.scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler
 from gpustack_b200.server import create_app
 from gpustack_b200.tokenizer import ByteTokenizer
 
@@ -47,7 +47,11 @@ class StubEngine:
         if plan is None:
             return None
         time.sleep(0.001)
-        if isinstance(plan, PrefillPlan):
+        if isinstance(plan, MixedPlan):
+            pre = [self._next(r) for r, s in zip(plan.prefill.reqs, plan.prefill.sample) if s]
+            dec = np.array([self._next(r) for r in self.sched.rows[:plan.batch]], dtype=np.int32)
+            out = self.sched.update_mixed(plan, pre, dec)
+        elif isinstance(plan, PrefillPlan):
             out = self.sched.update_prefill(plan, [self._next(r) for r, s in zip(plan.reqs, plan.sample) if s])
         else:
             toks = np.array([self._next(r) for r in self.sched.rows], dtype=np.int32)
@@ -353,6 +357,13 @@ def test_round_robin_relay_alternates_between_two_replicas_and_streams():
             th = threading.Thread(target=core.run, daemon=True)
             th.start()
             fronts.append(front); threads.append(th); ports.append(p)
+        for p in ports:      # both replicas RUNNING before they are handed to the relay (GPUStack routes to RUNNING instances only)
+            for _ in range(300):
+                try:
+                    if urllib.request.urlopen(f"http://127.0.0.1:{p}/health", timeout=1).status == 200:
+                        break
+                except Exception:
+                    time.sleep(0.1)
         rp = port()
         relay = subprocess.Popen([sys.executable, str(root / "tools" / "rr_relay.py"), "--port", str(rp), "--model", "stub-model"] +
                                  [f"http://127.0.0.1:{p}" for p in ports])

@@ -26,9 +26,13 @@ class FakeRunner:
                            np.asarray(table[:B]).tolist()))
         return np.arange(B, dtype=np.int32)
 
-    def prefill(self, chunks, starts, tables, sample):
-        self.calls.append(("prefill", [list(map(int, c)) for c in chunks], list(map(int, starts)),
-                           [list(map(int, t)) for t in tables], [bool(s) for s in sample]))
+    def prefill(self, chunks, starts, tables, sample, decode=None):
+        call = ("prefill", [list(map(int, c)) for c in chunks], list(map(int, starts)),
+                [list(map(int, t)) for t in tables], [bool(s) for s in sample])
+        if decode is not None:     # mixed step: decode rows ride along
+            B, last, comp, tab = decode
+            call += ((int(B), np.asarray(last[:B]).tolist(), np.asarray(comp[:B]).tolist(), np.asarray(tab[:B]).tolist()),)
+        self.calls.append(call)
         return np.zeros(sum(bool(s) for s in sample), dtype=np.int32)
 
 
@@ -48,6 +52,7 @@ def _worker(rank, port, q):
     steps = [
         ("decode", 3, [7, 8, 9], [20, 33, 5], [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]]),
         ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False]),
+        ("mixed", [[11, 12, 13]], [32], [[1, 5, 6]], [True], 2, [40, 41], [7, 19], [[2, 0, 0, 0, 0, 0], [3, 4, 0, 0, 0, 0]]),
     ]
     if rank == 0:
         for s in steps:
@@ -55,6 +60,8 @@ def _worker(rank, port, q):
                 _, B, last, comp, tab = s
                 payload = np.concatenate([np.array(last), np.array(comp), np.array(tab).reshape(-1)]).astype(np.int32)
                 tp.bcast_step([E._KIND_DECODE, B], payload)
+            elif s[0] == "mixed":
+                eng._bcast_prefill(s[1], s[2], s[3], s[4], (s[5], np.array(s[6]), np.array(s[7]), np.array(s[8])))
             else:
                 eng._bcast_prefill(s[1], s[2], s[3], s[4])
         eng.sync_mark(); eng.sync_mark()
@@ -83,6 +90,8 @@ def test_step_broadcast_roundtrip():
     assert calls[0] == ("decode", 3, [7, 8, 9], [20, 33, 5],
                         [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]])
     assert calls[1] == ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False])
+    assert calls[2] == ("prefill", [[11, 12, 13]], [32], [[1, 5, 6]], [True],
+                        (2, [40, 41], [7, 19], [[2, 0, 0, 0, 0, 0], [3, 4, 0, 0, 0, 0]]))
 
 
 def _stress(rank, port, q, channel):
