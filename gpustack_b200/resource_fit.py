@@ -48,7 +48,7 @@ class VramEstimate:
 
 
 def weight_bytes_per_gpu(m: ModelConfig, tp: int, quantization: Optional[str] = None) -> int:
-    """Resident weight bytes of one rank (embedding replicated, lm_head vocab-parallel, norms replicated)."""
+    """Resident weight bytes of one rank (embedding and lm_head vocab-parallel, norms replicated)."""
     H, I, L = m.hidden_size, m.intermediate_size, m.num_hidden_layers
     q = quantization or m.quantization
     lin_b = 1 if q == "fp8" else 2
@@ -60,9 +60,9 @@ def weight_bytes_per_gpu(m: ModelConfig, tp: int, quantization: Optional[str] = 
         mlp, router = 3 * I * H // tp, 0
     bias = (m.q_size + 2 * m.kv_size) // tp * 2 if m.attention_bias else 0
     per_layer = (attn + mlp) * lin_b + router + bias + 2 * H * 2 + (16 if q == "fp8" else 0)
-    embed = m.vocab_size * H * 2
     vocab_local = math.ceil(m.vocab_size / tp)
-    lm_head = 0 if m.tie_word_embeddings else vocab_local * H * 2     # tied: a view of the embedding table
+    embed = vocab_local * H * 2
+    lm_head = 0 if m.tie_word_embeddings else vocab_local * H * 2     # tied: the embedding shard itself
     return L * per_layer + embed + lm_head + H * 2
 
 

@@ -232,33 +232,51 @@ class ModelRunner:
             return self.twoshot.stage(T)
         return self.hbuf[:T]
 
-    def _tp_reduce_norm(self, T: int, norm_w: torch.Tensor) -> None:
-        """xn[:T] = rmsnorm(sum over ranks of the partial + resid) * norm_w; resid updated."""
+    def _tp_reduce_norm(self, T: int, norm_w: torch.Tensor, first: bool = False) -> None:
+        """xn[:T] = rmsnorm(sum over ranks of the partial + resid) * norm_w; resid updated.
+        first=True: the partial is the vocab-parallel embedding lookup and there is no residual yet
+        (resid := the summed embeddings)."""
         eps = self.mcfg.rms_norm_eps
+        res_in = None if first else self.resid[:T]
         if self._tp_mode == "oneshot":
             # ONE kernel pulls every rank's partial over NVLink, sums, adds the residual, normalises
             which = self._ar_toggle
             self._ar_toggle ^= 1
-            self.oneshot.allreduce_add_rms_norm(which, self.resid[:T], norm_w, self.xn[:T], self.resid[:T], T, eps)
+            self.oneshot.allreduce_add_rms_norm(which, res_in, norm_w, self.xn[:T], self.resid[:T], T, eps)
             self.stats["kernel_launches"] += 1
         elif self._tp_mode == "twoshot":
-            self.twoshot.rs_norm_ag(self.resid[:T], norm_w, self.resid[:T], T, eps)
+            self.twoshot.rs_norm_ag(res_in, norm_w, self.resid[:T], T, eps)
             self.stats["kernel_launches"] += 1
+        elif first:
+            torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
+            self.resid[:T].copy_(self.hbuf[:T])
+            ops.rms_norm(self.resid[:T], norm_w, eps, out=self.xn[:T])
+            self.stats["kernel_launches"] += 3
         else:
             torch.distributed.all_reduce(self.hbuf[:T], group=self.tp_group)
             ops.fused_add_rms_norm(self.hbuf[:T], self.resid[:T], norm_w, eps, out=self.xn[:T],
                                    residual_out=self.resid[:T])
             self.stats["kernel_launches"] += 2
 
-    def _layers(self, T: int, attn_fn) -> None:
-        """Runs all decoder layers over self.resid[:T] (already holding the embeddings); leaves the
-        final-normed hidden states in self.xn[:T]."""
+    def _embed(self, ids: torch.Tensor, T: int) -> None:
+        """Token embeddings -> resid[:T] and the first norm -> xn[:T].  TP: vocab-parallel lookup
+        (rows outside this rank's shard contribute zeros), summed by the step's first fused
+        all-reduce + RMSNorm (VocabParallelEmbedding + all-reduce of the reference engine)."""
         m, w = self.mcfg, self.w
         if self.tp > 1:
             self._tp_select_mode(T)
+            ops.embedding(ids, w.embed, out=self._tp_partial_out(T), vocab_start=w.vocab_start, vocab_end=w.vocab_end)
+            self._tp_reduce_norm(T, w.layers[0].input_norm, first=True)
+        else:
+            ops.embedding(ids, w.embed, out=self.resid[:T])
+            ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
+        self.stats["kernel_launches"] += 2
+
+    def _layers(self, T: int, attn_fn) -> None:
+        """Runs all decoder layers after self._embed() (resid[:T] = embeddings, xn[:T] = first norm);
+        leaves the final-normed hidden states in self.xn[:T]."""
+        m, w = self.mcfg, self.w
         pos, slots = self._pos, self._slots
-        ops.rms_norm(self.resid[:T], w.layers[0].input_norm, m.rms_norm_eps, out=self.xn[:T])
-        self.stats["kernel_launches"] += 2   # embedding (by the caller) + this norm
         for l, lw in enumerate(w.layers):
             if self.fp8:
                 self._layer_fp8(T, l, lw, attn_fn)
@@ -363,7 +381,7 @@ class ModelRunner:
         self._slots = sd[self.d_slots:self.d_slots + B]
         lens = sd[self.d_lens:self.d_lens + B]
         bt = sd[self.d_bt:self.d_bt + B * self.max_blocks].view(B, self.max_blocks)
-        ops.embedding(ids, self.w.embed, out=self.resid[:B])
+        self._embed(ids, B)
         splits, ws = self._decode_attn_plan(B)
 
         def attn(l):
@@ -506,7 +524,7 @@ class ModelRunner:
         ts_d, tq_d = sd[o_ts:o_ts + nt], sd[o_tq:o_tq + nt]
         bt_all = sd[o_bt:end].view(S + Bd, self.max_blocks)
         bt_d = bt_all[:S]
-        ops.embedding(ids, self.w.embed, out=self.resid[:T])
+        self._embed(ids, T)
         if Bd:
             dl_d, dbt_d = sd[o_dl:o_dl + Bd], bt_all[S:]
             splits, ws = self._decode_attn_plan(Bd)

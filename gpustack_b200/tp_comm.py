@@ -87,7 +87,8 @@ class TwoShotAllReduce:
     def rs_norm_ag(self, residual, w, residual_out, T: int, eps: float) -> None:
         """xn[:T] (on every rank) = rmsnorm(sum_r stage_r + residual) * w; residual rows of this rank updated."""
         check(self.lib.b200_allreduce_rs_norm_ag(self._stage, self._xn, self._flags, self.world, self.rank,
-                                                 residual.data_ptr(), w.data_ptr(), residual_out.data_ptr(), T, self.H,
+                                                 None if residual is None else residual.data_ptr(), w.data_ptr(),
+                                                 residual_out.data_ptr(), T, self.H,
                                                  eps, torch.cuda.current_stream().cuda_stream), "allreduce_rs_norm_ag")
 
     def close(self) -> None:

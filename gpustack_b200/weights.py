@@ -4,7 +4,7 @@ fp8 W8A8) tensors.
 Sharding follows the reference engine's Megatron layout (SURVEY.md section 8e;
 $VLLM/model_executor/models/llama.py:81-347): QKV and gate_up are column-parallel (each rank owns
 Hq/t query heads, Hkv/t kv heads and I/t MLP columns), O and down are row-parallel (in-dim / t),
-lm_head is vocab-parallel, the embedding table and the norms are replicated.
+lm_head and the embedding table are vocab-parallel (rows [rank*ceil(V/t), ...)), the norms are replicated.
 
 fp8 (`--quantization fp8`, or a checkpoint whose config.json carries quantization_config
 {quant_method: fp8, activation_scheme: dynamic}): the four decoder linears of every layer are held
@@ -54,7 +54,7 @@ class LayerWeights:
 
 @dataclass
 class ModelWeights:
-    embed: torch.Tensor           # [V, H] replicated
+    embed: torch.Tensor           # [V/t, H]: this rank's vocabulary rows (the whole table when t == 1)
     layers: List[LayerWeights]
     final_norm: torch.Tensor      # [H]
     lm_head: torch.Tensor         # [V/t (padded to a multiple of 8), H]
@@ -181,12 +181,14 @@ def shard_state_dict(cfg: ModelConfig, get: Callable[[str], torch.Tensor], rank:
             post_norm=dev(get(p + "post_attention_layernorm.weight")),
             gate_up=gu_w, down=down_w,
             qkv_scale=qkv_s, o_scale=o_s, gate_up_scale=gu_s, down_scale=down_s, **moe))
-    embed = dev(get("model.embed_tokens.weight"))
     V = cfg.vocab_size
     per = (V + tp - 1) // tp
     v0, v1 = rank * per, min(V, (rank + 1) * per)
-    # tied embeddings: the vocab shard is a row-range VIEW of the replicated table (no second copy)
-    lm = embed[v0:v1] if cfg.tie_word_embeddings else dev(get("lm_head.weight")[v0:v1])
+    # vocab-parallel embedding (VocabParallelEmbedding of the reference engine): each rank looks up
+    # only its own rows, the partial result is summed by the first fused all-reduce + norm of the step
+    embed = dev(get("model.embed_tokens.weight")[v0:v1])
+    # tied embeddings: the lm_head shard IS the embedding shard (no second copy)
+    lm = embed if cfg.tie_word_embeddings else dev(get("lm_head.weight")[v0:v1])
     return ModelWeights(embed=embed, layers=layers, final_norm=dev(get("model.norm.weight")),
                         lm_head=lm, vocab_start=v0, vocab_end=v1)
 

@@ -71,3 +71,20 @@ def test_registration_rules():
     errs = gc.validate_backend(bad)
     assert any("-custom" in e for e in errs) and any("custom_framework" in e for e in errs)
     assert any("health_check_path" in e for e in errs)
+
+
+def test_first_class_backend_binding_compiles():
+    """deploy/first_class_backend/b200_native.py is the reference-side binding a GPUStack maintainer
+    would add (BackendEnum / _SERVER_CLASS_MAPPING / selector switch).  gpustack.* cannot be imported
+    offline, so it is compiled, and the engine-side names it calls must exist."""
+    import ast
+
+    src = (ROOT / "deploy" / "first_class_backend" / "b200_native.py").read_text()
+    tree = ast.parse(src)
+    classes = {n.name for n in tree.body if isinstance(n, ast.ClassDef)}
+    assert {"B200NativeServer", "B200NativeResourceFitSelector"} <= classes
+    from gpustack_b200.config import tiny_llama, EngineConfig
+    from gpustack_b200.resource_fit import estimate
+
+    est = estimate(tiny_llama(), EngineConfig(tensor_parallel_size=2))
+    assert est.total_min == est.per_gpu_min * 2 and est.total_min > 0
