@@ -9,7 +9,8 @@
 // (sequence, kv-head, split); the G = Hq/Hkv query heads of the group form the M rows of
 // mma.sync m16n8k16, so every K/V byte is fetched from HBM once per group.  Each of the 4 warps
 // owns an independent 3-stage cp.async ring over its pages (2 CTAs/SM -> ~128 KB in flight per
-// SM), runs an online softmax in fp32, and the warps / splits are merged at the end.
+// SM), runs an online softmax in fp32; warps are merged in shared memory, KV splits by the last CTA
+// of the (sequence, kv-head) group to finish (arrival counter in the workspace) -- no merge launch.
 //
 // Prefill kernel: causal, ragged, chunk-capable.  One CTA per (query tile, kv-head); warp w
 // holds 16 query tokens of one head of the group, K/V are streamed in 64-token chunks through a
@@ -63,7 +64,7 @@ paged_attn_decode_kernel(const bf16* __restrict__ q, int64_t q_stride,
                          const int32_t* __restrict__ block_table, int max_blocks,
                          const int32_t* __restrict__ seq_lens, bf16* __restrict__ out,
                          float* __restrict__ ws_o, float* __restrict__ ws_ml, int num_splits,
-                         int Hq, int Hkv, float scale_log2) {
+                         int Hq, int Hkv, float scale_log2, uint32_t* __restrict__ split_ctr) {
   pdl_launch_dependents();
   pdl_wait();
   using Cfg = DecCfg<D>;
@@ -249,38 +250,38 @@ paged_attn_decode_kernel(const bf16* __restrict__ q, int64_t q_stride,
       if (d == 0) { ws_ml[slot * 2] = mm; ws_ml[slot * 2 + 1] = den; }
     }
   }
-}
-
-// merge the per-split partials: one warp per (b, head)
-template <int D>
-__global__ void __launch_bounds__(128)
-attn_merge_splits_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml,
-                         bf16* __restrict__ out, int num_splits, int rows) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* ml = ws_ml + (size_t)row * num_splits * 2;
-  float mm = -INFINITY;
-  for (int s = 0; s < num_splits; ++s) mm = fmaxf(mm, ml[s * 2]);
-  float den = 0.f;
-  float acc[D / 32];
-#pragma unroll
-  for (int j = 0; j < D / 32; ++j) acc[j] = 0.f;
-  for (int s = 0; s < num_splits; ++s) {
-    const float m = ml[s * 2];
-    if (m == -INFINITY) continue;
-    const float sc = exp2f(m - mm);
-    den += sc * ml[s * 2 + 1];
-    const float* o = ws_o + ((size_t)row * num_splits + s) * D;
-#pragma unroll
-    for (int j = 0; j < D / 32; ++j) acc[j] += sc * o[lane + 32 * j];
+  if (num_splits == 1) return;
+  // ---- cross-split merge by the LAST CTA of this (sequence, kv-head) to arrive: no extra launch.
+  // Every CTA publishes its partials (release), bumps the group's counter, and the one that sees
+  // num_splits - 1 earlier arrivals reads all partials back (L2) and writes the final rows; it
+  // also resets the counter, so the workspace is reusable by the next launch / graph replay.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(split_ctr + (size_t)b * Hkv + kvh, 1u);
+    s_last = (prev == (uint32_t)(num_splits - 1));
+    if (s_last) split_ctr[(size_t)b * Hkv + kvh] = 0u;
   }
-  const float inv = den > 0.f ? 1.f / den : 0.f;
-#pragma unroll
-  for (int j = 0; j < D / 32; ++j)
-    out[(size_t)row * D + lane + 32 * j] = __float2bfloat16_rn(acc[j] * inv);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+    const int g = idx / D, d = idx % D;
+    const size_t row = (size_t)b * Hq + kvh * G + g;
+    const float* ml = ws_ml + row * num_splits * 2;
+    float mm = -INFINITY;
+    for (int sp = 0; sp < num_splits; ++sp) mm = fmaxf(mm, __ldcg(ml + sp * 2));
+    float num = 0.f, den = 0.f;
+    for (int sp = 0; sp < num_splits; ++sp) {
+      const float m = __ldcg(ml + sp * 2);
+      if (m == -INFINITY) continue;
+      const float sc = exp2f(m - mm);
+      den += sc * __ldcg(ml + sp * 2 + 1);
+      num += sc * __ldcg(ws_o + (row * num_splits + sp) * D + d);
+    }
+    out[row * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+  }
 }
 
 // ----------------------------------------------------------------------------------- prefill
@@ -677,9 +678,15 @@ extern "C" int b200_attn_decode_splits(int B, int Hkv, int max_seq_len, int bloc
   return want < 1 ? 1 : want;
 }
 
+// partial O [B*Hq*splits][D] + (m, l) [B*Hq*splits][2] fp32, then one arrival counter per (sequence,
+// kv-head) group.  The counters sit at the START of the workspace (zeroed once by the caller,
+// b200_attn_decode_workspace_init; self-resetting afterwards) so that one buffer sized for the worst
+// batch serves every batch size.
+static size_t attn_decode_ctr_bytes(int B, int Hq) { return ((size_t)B * Hq * sizeof(uint32_t) + 255) & ~(size_t)255; }
+
 extern "C" size_t b200_attn_decode_workspace_bytes(int B, int Hq, int D, int num_splits) {
   if (num_splits <= 1) return 16;
-  return (size_t)B * Hq * num_splits * (size_t)(D + 2) * sizeof(float);
+  return attn_decode_ctr_bytes(B, Hq) + (size_t)B * Hq * num_splits * (size_t)(D + 2) * sizeof(float);
 }
 
 extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const void* k_cache,
@@ -696,7 +703,11 @@ extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const voi
   if (B == 0) return B200_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const float scale_log2 = scale * 1.4426950408889634f;
-  float* ws_o = reinterpret_cast<float*>(workspace);
+  // counters live in the first bytes of the workspace, sized for THIS call's B (<= the B the buffer was
+  // sized and zeroed for: a prefix of a zeroed, self-resetting array is itself zeroed)
+  uint32_t* split_ctr = reinterpret_cast<uint32_t*>(workspace);
+  float* ws_o = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + attn_decode_ctr_bytes(B, Hq))
+                          : nullptr;
   float* ws_ml = ws_o ? ws_o + (size_t)B * Hq * num_splits * D : nullptr;
   dim3 grid(Hkv, num_splits, B);
   int rc;
@@ -709,15 +720,8 @@ extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const voi
     }
     (void)launch_pdl(paged_attn_decode_kernel<128>, dim3(grid), dim3(kDecWarps * 32), DecCfg<128>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
-        max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2);
+        max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2, split_ctr);
     rc = b200_check_launch("b200_paged_attn_decode");
-    if (rc) return rc;
-    if (num_splits > 1) {
-      const int rows = B * Hq;
-      (void)launch_pdl(attn_merge_splits_kernel<128>, dim3((rows + 3) / 4), dim3(128), 0, s, 1, ws_o, ws_ml, (bf16*)out,
-                                                                  num_splits, rows);
-      rc = b200_check_launch("b200_paged_attn_decode(merge)");
-    }
   } else {
     static bool once = false;
     if (!once) {
@@ -727,15 +731,8 @@ extern "C" int b200_paged_attn_decode(const void* q, int64_t q_stride, const voi
     }
     (void)launch_pdl(paged_attn_decode_kernel<64>, dim3(grid), dim3(kDecWarps * 32), DecCfg<64>::kSmemBytes, s, 1, 
         (const bf16*)q, q_stride, (const bf16*)k_cache, (const bf16*)v_cache, block_table,
-        max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2);
+        max_blocks, seq_lens, (bf16*)out, ws_o, ws_ml, num_splits, Hq, Hkv, scale_log2, split_ctr);
     rc = b200_check_launch("b200_paged_attn_decode");
-    if (rc) return rc;
-    if (num_splits > 1) {
-      const int rows = B * Hq;
-      (void)launch_pdl(attn_merge_splits_kernel<64>, dim3((rows + 3) / 4), dim3(128), 0, s, 1, ws_o, ws_ml, (bf16*)out,
-                                                                 num_splits, rows);
-      rc = b200_check_launch("b200_paged_attn_decode(merge)");
-    }
   }
   return rc;
 }

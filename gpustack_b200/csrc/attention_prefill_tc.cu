@@ -51,7 +51,12 @@ constexpr int kFaMaxSlack = kFaSmemBytes - kFaOffBar - 256;
 constexpr int kFaTmemCols = 256;                       // S0 [0,64)  S1 [64,128)  O [128,256)
 constexpr float kFaRescaleThreshold = 8.f;             // log2 units
 
-template <int G>
+// P_TMEM: P_j is written back into the first 32 columns of the TMEM buffer S_j came from (bf16 pairs
+// per 32-bit column, tcgen05.st) and the PV MMA reads its A operand from tensor memory: no shared-
+// memory round trip, no proxy fence, and the softmax of block j+1 no longer waits for PV_j to retire
+// (it only ever waits for p_empty when the O accumulator has to be rescaled).  P_TMEM = false keeps
+// P in swizzled shared memory (B200_ATTN_P_TMEM=0, A/B runs).
+template <int G, bool P_TMEM>
 __global__ void __launch_bounds__(kFaThreads, 2)
 paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const __grid_constant__ CUtensorMap tmap_k,
@@ -198,9 +203,14 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         const uint32_t v_addr = kv_addr + slot * kFaSlotBytes;
 #pragma unroll
-        for (int k = 0; k < kFaKv / kUmmaKBf16; ++k)     // 4 MMAs x 16 KV tokens
-          umma_bf16(tmem_base + 2 * kFaKv, umma_desc_k_sw128(p_addr + k * 32),
-                    umma_desc_mn_sw128(v_addr + k * (kUmmaKBf16 * 128), kFaHalfBytes, 1024), idesc_o, (j | k) != 0);
+        for (int k = 0; k < kFaKv / kUmmaKBf16; ++k) {   // 4 MMAs x 16 KV tokens
+          const uint64_t v_desc = umma_desc_mn_sw128(v_addr + k * (kUmmaKBf16 * 128), kFaHalfBytes, 1024);
+          if constexpr (P_TMEM)   // A = P_j in TMEM: 16 bf16 of K = 8 columns per MMA
+            umma_bf16_ts(tmem_base + 2 * kFaKv, tmem_base + (uint32_t)((j & 1) * kFaKv + k * 8), v_desc, idesc_o,
+                         (j | k) != 0);
+          else
+            umma_bf16(tmem_base + 2 * kFaKv, umma_desc_k_sw128(p_addr + k * 32), v_desc, idesc_o, (j | k) != 0);
+        }
         umma_commit(&kv_empty[slot]);     // V_j slot reusable
         umma_commit(p_empty);             // P buffer and the O accumulator are stable again
       }
@@ -265,11 +275,12 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
         pk[16 + (c >> 1)] = pack_bf16(p2, p3);
       }
       l += sum;
-      if (j > 0) {   // PV_{j-1} has retired: P may be overwritten, O may be rescaled
+      const bool any_rescale = __any_sync(0xffffffffu, rescale);
+      if (j > 0 && (!P_TMEM || any_rescale)) {   // PV_{j-1} has retired: smem P may be overwritten, O may be rescaled
         mbar_wait_guarded(p_empty, (j - 1) & 1);
         tc_fence_after();
       }
-      if (__any_sync(0xffffffffu, rescale)) {
+      if (any_rescale) {
 #pragma unroll 1
         for (int c4 = 0; c4 < kFaD / 32; ++c4) {
           uint32_t o[32];
@@ -281,12 +292,18 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         tmem_st_wait();
       }
-      // P row (64 bf16 = 8 chunks of 16 B) into the 128B-swizzled K-major A-operand layout
+      if constexpr (P_TMEM) {
+        // P row (64 bf16 = 32 packed columns) over the first half of the S_j buffer this thread just read
+        tmem_st_32x32(t_lane + (uint32_t)((j & 1) * kFaKv), pk);
+        tmem_st_wait();
+      } else {
+        // P row (64 bf16 = 8 chunks of 16 B) into the 128B-swizzled K-major A-operand layout
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        st_shared_v4(p_row + (((uint32_t)ch ^ sw) << 4),
-                     make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
-      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(p_row + (((uint32_t)ch ^ sw) << 4),
+                       make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -324,13 +341,13 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
-template <int G>
+template <int G, bool P_TMEM>
 static int launch_prefill_tc(const void* q, int64_t q_stride, int num_tokens, const void* k_cache,
                              const void* v_cache, int num_blocks, const int32_t* block_table, int max_blocks,
                              const int32_t* cu_q, const int32_t* ctx_lens, const int32_t* tile_seq,
                              const int32_t* tile_q0, int num_tiles, void* out, int Hq, int Hkv, float scale,
                              cudaStream_t stream) {
-  auto kernel = paged_attn_prefill_tc_kernel<G>;
+  auto kernel = paged_attn_prefill_tc_kernel<G, P_TMEM>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes);
@@ -377,11 +394,17 @@ int paged_attn_prefill_tc(const void* q, int64_t q_stride, int num_tokens, const
   const DeviceInfo& d = device_info();
   if (!enabled || D != kFaD || (G != 4 && G != 8) || !d.valid || d.cc_major != 10) return 1;
   if (num_tokens <= 0 || num_blocks <= 0 || (q_stride % 8) != 0) return 1;
-  if (G == 4)
-    return launch_prefill_tc<4>(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table, max_blocks, cu_q,
-                                ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv, scale, stream);
-  return launch_prefill_tc<8>(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table, max_blocks, cu_q,
-                              ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv, scale, stream);
+  static int p_tmem = -1;
+  if (p_tmem < 0) {
+    const char* e = getenv("B200_ATTN_P_TMEM");   // =0: P through shared memory (A/B runs)
+    p_tmem = (e && e[0] == '0') ? 0 : 1;
+  }
+#define B200_FA_LAUNCH(GG, PT)                                                                                       \
+  launch_prefill_tc<GG, PT>(q, q_stride, num_tokens, k_cache, v_cache, num_blocks, block_table, max_blocks, cu_q,    \
+                            ctx_lens, tile_seq, tile_q0, num_tiles, out, Hq, Hkv, scale, stream)
+  if (G == 4) return p_tmem ? B200_FA_LAUNCH(4, true) : B200_FA_LAUNCH(4, false);
+  return p_tmem ? B200_FA_LAUNCH(8, true) : B200_FA_LAUNCH(8, false);
+#undef B200_FA_LAUNCH
 }
 
 }  // namespace b200

@@ -347,7 +347,9 @@ def attn_decode_splits(B, Hkv, max_seq_len) -> int:
 
 def attn_decode_workspace(B, Hq, D, num_splits, device) -> torch.Tensor:
     n = load().b200_attn_decode_workspace_bytes(B, Hq, D, num_splits)
-    return torch.empty((n + 3) // 4, dtype=torch.float32, device=device)
+    # zeroed ONCE: the first bytes hold the per-(sequence, kv-head) arrival counters of the in-kernel
+    # split merge, which reset themselves after every launch
+    return torch.zeros((n + 3) // 4, dtype=torch.float32, device=device)
 
 
 def paged_attn_decode(q, q_stride, k_cache, v_cache, block_table, seq_lens, out, Hq, Hkv, D, scale,

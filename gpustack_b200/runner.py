@@ -149,7 +149,8 @@ class ModelRunner:
             need = max(L.b200_attn_decode_workspace_bytes(b, self.Hq, self.D,
                                                           ops.attn_decode_splits(b, self.Hkv, self.max_model_len))
                        for b in range(1, self.max_seqs + 1))
-            self._attn_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            # zeroed once: it starts with the self-resetting arrival counters of the in-kernel split merge
+            self._attn_ws = torch.zeros((need + 3) // 4, dtype=torch.float32, device=self.device)
         return splits, self._attn_ws
 
     def kv_block_bytes(self) -> int:
@@ -388,8 +389,6 @@ class ModelRunner:
             ops.paged_attn_decode(self.qkv[:B], self.qkv_width, self.k_cache[l], self.v_cache[l], bt, lens,
                                   self.attn_out[:B], self.Hq, self.Hkv, self.D, self.scale,
                                   num_splits=splits, workspace=ws)
-            if splits > 1:
-                self.stats["kernel_launches"] += 1   # split merge kernel
 
         self._layers(B, attn)
         self._sample(B, None)
@@ -538,7 +537,7 @@ class ModelRunner:
                 ops.paged_attn_decode(self.qkv[Tp:T], self.qkv_width, self.k_cache[l], self.v_cache[l], dbt_d, dl_d,
                                       self.attn_out[Tp:T], self.Hq, self.Hkv, self.D, self.scale,
                                       num_splits=splits, workspace=ws)
-                self.stats["kernel_launches"] += 1 + (splits > 1)
+                self.stats["kernel_launches"] += 1
 
         self._layers(T, attn)
         self.stats["prefill_steps"] += 1

@@ -161,7 +161,9 @@ int b200_gemm_suggest_splits(int M, int N, int K);
 /* ---- paged-KV attention: $VLLM/v1/attention/backends/flashinfer.py:1095-1230 -------------- */
 /* Decode: one query token per sequence.  q [B, Hq, D] bf16 with row stride q_stride (elements),
  * out [B, Hq*D] bf16, block_table [B, max_blocks] int32, seq_lens [B] int32 (incl. the new
- * token).  workspace: fp32 scratch of b200_attn_decode_workspace_bytes(); num_splits from
+ * token).  workspace: b200_attn_decode_workspace_bytes() bytes, ZEROED ONCE by the caller before its
+ * first use (it starts with the self-resetting arrival counters of the in-kernel split merge; a
+ * buffer sized for a larger batch may be reused for smaller ones); num_splits from
  * b200_attn_decode_splits() or caller-chosen (>=1). */
 int b200_attn_decode_splits(int B, int Hkv, int max_seq_len, int block_size);
 size_t b200_attn_decode_workspace_bytes(int B, int Hq, int D, int num_splits);

@@ -20,7 +20,7 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 mcfg = llama3_8b()
 eng = LLMEngine.from_engine_config(
     EngineConfig(max_num_seqs=R, max_num_batched_tokens=8192, max_model_len=1024, enforce_eager=True,
-                 num_gpu_blocks=R * 48 + 64), mcfg=mcfg)
+                 num_gpu_blocks=R * 48 + 64, mixed_steps=False), mcfg=mcfg)   # pure prefill / pure decode steps
 rs = np.random.RandomState(0)
 prompts = rs.randint(256, mcfg.vocab_size - 256, size=(R, 512)).tolist()
 sp = SamplingParams(max_tokens=6, ignore_eos=True)
