@@ -669,8 +669,13 @@ extern "C" int b200_attn_decode_splits(int B, int Hkv, int max_seq_len, int bloc
   if (B <= 0 || Hkv <= 0 || max_seq_len <= 0 || block_size <= 0) return 1;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int pages = (max_seq_len + block_size - 1) / block_size;
-  const int base = B * Hkv;
-  int want = (2 * 2 * sms + base - 1) / base;  // 2 CTAs/SM, 2 waves
+  const int base = B * Hkv;                     // CTAs without splitting
+  const int slots = 2 * sms;                    // resident CTAs (2 per SM)
+  // one wave is enough once the unsplit grid nearly fills the machine: a split costs every CTA its
+  // fixed part (Q staging, in-CTA merge, partials) again -- measured on the TP=8 shard shape
+  // (B=256, one kv-head per rank) 3 splits ran at 0.3 of the HBM roofline
+  if (base * 4 >= slots * 3) return 1;
+  int want = (2 * slots + base - 1) / base;     // otherwise: about two waves
   int cap = pages / 8;                          // >= 8 pages (2 per warp) per split
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
