@@ -65,6 +65,8 @@ def parse_args():
                     help="wall-clock budget of the whole run; optional legs are skipped / bounded to stay inside it")
     ap.add_argument("--cpu-sample-requests", type=int, default=2)
     ap.add_argument("--cpu-sample-output", type=int, default=16)
+    ap.add_argument("--no-cpu-configs0", action="store_true",
+                    help="skip the BASELINE configs[0] CPU leg (Qwen2-0.5B shape, 32 requests on the host cores)")
     return ap.parse_args()
 
 
@@ -675,6 +677,16 @@ def run_ours(a):
                                "p50_ttft_ms": t,
                                "sample": f"{a.cpu_sample_requests} requests x {a.input_len} in / {a.cpu_sample_output} out, "
                                          f"sequential, {dt:.1f} s of CPU work (oracle/llama_oracle.py, fp32 math)"}
+        if not a.no_cpu_configs0 and a.time_budget_s - (time.time() - _T0) > 420:
+            # BASELINE.json configs[0]: the reference's CPU-runnable case -- Qwen2-0.5B shape,
+            # the full 32 requests of the plumbing run, on this box's host cores, in this same run
+            log("CPU baseline, configs[0]: Qwen2-0.5B shape x 32 requests ...")
+            v0, t0_, dt0 = cpu_reference("qwen2-0.5b", 32, 64, 8)
+            res["cpu_baseline"]["configs0"] = {
+                "model": "Qwen2-0.5B shape (random init; llama-box / GGUF unavailable offline: oracle port)", "value": v0,
+                "unit": UNIT, "p50_ttft_ms": t0_, "cores": torch.get_num_threads(),
+                "sample": f"32 requests x 64 in / 8 out, sequential, {dt0:.1f} s of CPU work"}
+            log(f"cpu configs[0]: {v0:.1f} tok/s in {dt0:.1f}s")
     return res
 
 
