@@ -102,29 +102,54 @@ splitk_reduce_kernel(const float* __restrict__ P, int S, bf16* __restrict__ Y, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Greedy sampler: lowest index of the row maximum.  One CTA per row.
+// Sampler: one CTA per row, ONE pass over the fp32 logits.
+//   temperature 0 (or temps == nullptr): greedy -- lowest index of the row maximum;
+//   temperature T > 0: exact softmax(logits / T) sampling by the Gumbel-max trick,
+//       token = argmax_v ( logit_v / T - log(-log(u_v)) ),  u_v = hash(row seed, GLOBAL vocab index),
+//     so sampling costs what greedy costs, stays inside the captured decode graph, and composes with
+//     vocabulary-parallel logits: every rank perturbs its shard with noise keyed by the global index and
+//     the cross-rank (max, argmax) exchange that serves greedy picks the sampled token.
+//     (Reference: $VLLM/v1/sample/sampler.py draws from softmax(logits / T); nucleus (top_p < 1) rows are
+//     re-sampled by the host path.)  The row seed changes every step (request seed x position).
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ float gumbel_key(float logit, float inv_t, uint32_t seed, uint32_t gidx) {
+  const uint32_t h = fmix32(fmix32(gidx * 0x9e3779b1u + seed) ^ (seed * 0x85ebca6bu + 0x632be5abu));
+  const float u = ((float)(h >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+  return logit * inv_t - __logf(-__logf(u));
+}
+
 __global__ void __launch_bounds__(1024)
 argmax_f32_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __restrict__ out_idx,
-                  float* __restrict__ out_val, int V) {
+                  float* __restrict__ out_val, int V, const float* __restrict__ temps,
+                  const uint32_t* __restrict__ seeds, int vocab_offset) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   const float* row = logits + (size_t)blockIdx.x * ld;
+  const float temp = temps ? temps[blockIdx.x] : 0.f;
+  const bool sample = temp > 0.f;
+  const float inv_t = sample ? 1.f / temp : 1.f;
+  const uint32_t seed = (sample && seeds) ? seeds[blockIdx.x] : 0u;
   float best = -FLT_MAX;
   int best_i = 0x7fffffff;
   const int nvec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
   for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
     const float4 v = ld_cg_f4(reinterpret_cast<const float4*>(row) + vi);
-    const float f[4] = {v.x, v.y, v.z, v.w};
+    float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = vi * 4 + j;
+      if (sample) f[j] = gumbel_key(f[j], inv_t, seed, (uint32_t)(vocab_offset + i));
       if (f[j] > best || (f[j] == best && i < best_i)) { best = f[j]; best_i = i; }
     }
   }
   for (int i = nvec * 4 + threadIdx.x; i < V; i += blockDim.x) {
-    const float f = row[i];
+    float f = row[i];
+    if (sample) f = gumbel_key(f, inv_t, seed, (uint32_t)(vocab_offset + i));
     if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
   }
 #pragma unroll
@@ -209,6 +234,18 @@ extern "C" int b200_argmax_f32(const float* logits, int64_t ld, int32_t* out_idx
                                int B, int V, void* stream) {
   B200_REQUIRE(B >= 0 && V > 0, "argmax: bad shape");
   if (B == 0) return B200_OK;
-  (void)launch_pdl_cls(kPdlSampler, argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx, out_val, V);
+  (void)launch_pdl_cls(kPdlSampler, argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx,
+                       out_val, V, (const float*)nullptr, (const uint32_t*)nullptr, 0);
   return b200_check_launch("b200_argmax_f32");
+}
+
+// Greedy (temps[b] == 0) or Gumbel-max temperature sampling (temps[b] > 0, seed seeds[b]) of row b in one
+// pass; vocab_offset = global index of column 0 (vocabulary-parallel shards); out_val = the winning key.
+extern "C" int b200_sample_f32(const float* logits, int64_t ld, const float* temps, const uint32_t* seeds,
+                               int vocab_offset, int32_t* out_idx, float* out_val, int B, int V, void* stream) {
+  B200_REQUIRE(B >= 0 && V > 0 && vocab_offset >= 0, "sample: bad shape");
+  if (B == 0) return B200_OK;
+  (void)launch_pdl_cls(kPdlSampler, argmax_f32_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, 1, logits, ld, out_idx,
+                       out_val, V, temps, seeds, vocab_offset);
+  return b200_check_launch("b200_sample_f32");
 }

@@ -19,7 +19,8 @@ import torch
 from .config import EngineConfig, ModelConfig
 from .lib import B200Error
 from .runner import ModelRunner
-from .scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput
+from .scheduler import (DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput,
+                        kernel_temperature, step_seeds)
 from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, random_state_dict,
                       shard_state_dict)
 
@@ -272,12 +273,15 @@ class LLMEngine:
         if isinstance(plan, DecodePlan):
             B = plan.batch
             s = self.sched
+            temps = s.temperature[:B]
+            seeds = step_seeds(s.sample_seed[:B], s.num_computed[:B])
             if self.tp:
                 tb = time.perf_counter()
-                payload = np.concatenate([s.last_token[:B], s.num_computed[:B], s.block_table[:B].reshape(-1)])
+                payload = np.concatenate([s.last_token[:B], s.num_computed[:B], temps.view(np.int32), seeds.view(np.int32),
+                                          s.block_table[:B].reshape(-1)])
                 self.tp.bcast_step([_KIND_DECODE, B], payload.astype(np.int32))
                 self.step_time["decode_bcast"] = self.step_time.get("decode_bcast", 0.0) + time.perf_counter() - tb
-            toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table)
+            toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table, temps, seeds)
             toks = self._apply_sampling(list(s.rows[:B]), toks)
             out = s.update_decode(plan, toks)
             self.step_time["decode"] += time.perf_counter() - t0
@@ -289,10 +293,15 @@ class LLMEngine:
             dec = (B, s.last_token, s.num_computed, s.block_table) if mixed else None
             chunks = [r.all_ids[st:st + n] for r, st, n in zip(pre.reqs, pre.starts, pre.lens)]
             tables = [r.blocks for r in pre.reqs]
-            if self.tp:
-                self._bcast_prefill(chunks, pre.starts, tables, pre.sample, dec)
-            toks = self.runner.prefill(chunks, pre.starts, tables, pre.sample, decode=dec)
             sampled = [r for r, smp in zip(pre.reqs, pre.sample) if smp]
+            # in-kernel sampler inputs, one per sampled row: completed prompts first, then the riding decode rows
+            stemps = np.asarray([kernel_temperature(r.params) for r in sampled] + s.temperature[:B].tolist(), dtype=np.float32)
+            sseeds = np.concatenate([step_seeds([r.sample_seed for r in sampled], [r.prefill_target for r in sampled]),
+                                     step_seeds(s.sample_seed[:B], s.num_computed[:B])]).astype(np.uint32)
+            if self.tp:
+                self._bcast_prefill(chunks, pre.starts, tables, pre.sample, dec, stemps, sseeds)
+            toks = self.runner.prefill(chunks, pre.starts, tables, pre.sample, decode=dec, sample_temps=stemps,
+                                       sample_seeds=sseeds)
             toks = self._apply_sampling(sampled + list(s.rows[:B]), toks)
             ns = len(sampled)
             if mixed:
@@ -309,8 +318,9 @@ class LLMEngine:
         return out
 
     def _apply_sampling(self, reqs, toks):
-        """Override the in-graph greedy tokens of requests that asked for temperature > 0."""
-        rows = [i for i, r in enumerate(reqs) if r.params.temperature > 0.0]
+        """Plain temperature sampling happens in the sampler kernel (Gumbel-max, runner._sample); only
+        NUCLEUS requests (temperature > 0 and top_p < 1) are re-sampled here from the step's logits."""
+        rows = [i for i, r in enumerate(reqs) if r.params.temperature > 0.0 and r.params.top_p < 1.0]
         if not rows:
             return toks
         if self.tp is not None:      # every rank joins the all-gather of the vocab-sharded logits rows
@@ -328,7 +338,7 @@ class LLMEngine:
         toks[rows] = sampled
         return toks
 
-    def _bcast_prefill(self, chunks, starts, tables, sample, dec=None) -> None:
+    def _bcast_prefill(self, chunks, starts, tables, sample, dec=None, stemps=None, sseeds=None) -> None:
         S = len(chunks)
         lens = [len(c) for c in chunks]
         nb = [len(t) for t in tables]
@@ -338,8 +348,11 @@ class LLMEngine:
         if dec is not None:     # mixed step: the decode rows' (last token, position, block table) follow
             B, last, comp, bt = dec
             parts += [last[:B], comp[:B], bt[:B].reshape(-1)]
+        ns = 0 if stemps is None else len(stemps)
+        if ns:
+            parts += [np.asarray(stemps, dtype=np.float32).view(np.int32), np.asarray(sseeds, dtype=np.uint32).view(np.int32)]
         flat = np.concatenate([np.asarray(p).reshape(-1) for p in parts]).astype(np.int32)
-        self.tp.bcast_step([_KIND_MIXED if dec is not None else _KIND_PREFILL, S, B], flat)
+        self.tp.bcast_step([_KIND_MIXED if dec is not None else _KIND_PREFILL, S, B, ns], flat)
 
     def shutdown(self) -> None:
         if self.tp and self.tp.rank == 0:
@@ -418,7 +431,8 @@ class TPWorker:
                 continue
             if kind == _KIND_DECODE:
                 B = h[1]
-                run.decode(B, p[:B], p[B:2 * B], p[2 * B:].reshape(B, mb))
+                run.decode(B, p[:B], p[B:2 * B], p[4 * B:].reshape(B, mb), p[2 * B:3 * B].view(np.float32),
+                           p[3 * B:4 * B].view(np.uint32))
             else:
                 S = h[1]
                 lens, starts, sample, nb = p[:S], p[S:2 * S], p[2 * S:3 * S], p[3 * S:4 * S]
@@ -433,4 +447,9 @@ class TPWorker:
                 if kind == _KIND_MIXED:
                     B = h[2]
                     dec = (B, p[off:off + B], p[off + B:off + 2 * B], p[off + 2 * B:off + 2 * B + B * mb].reshape(B, mb))
-                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample], decode=dec)
+                    off += 2 * B + B * mb
+                ns = h[3]
+                st_ = p[off:off + ns].view(np.float32) if ns else None
+                ss_ = p[off + ns:off + 2 * ns].view(np.uint32) if ns else None
+                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample], decode=dec, sample_temps=st_,
+                            sample_seeds=ss_)

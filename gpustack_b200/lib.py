@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200_silu_and_mul": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "b200_embedding": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200_argmax_f32": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _vp]),
+    "b200_sample_f32": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "b200_gather_rows": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "b200_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _i32, _vp]),
     "b200_gemm_bf16_ex": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _vp]),

@@ -140,6 +140,17 @@ def argmax(logits, out_idx=None, out_val=None):
     return idx
 
 
+def sample(logits, temps, seeds, out_idx=None, out_val=None, vocab_offset: int = 0):
+    """Greedy (temps == 0) or Gumbel-max temperature sampling per row in ONE pass over the logits.
+    temps: fp32 [B]; seeds: int32/uint32 [B] (bit patterns); returns int32 token ids (shard-local)."""
+    _req(logits, torch.float32, "logits"); _req(temps, torch.float32, "temps"); _req(seeds, torch.int32, "seeds")
+    B, V = logits.shape
+    idx = torch.empty((B,), dtype=torch.int32, device=logits.device) if out_idx is None else out_idx
+    check(load().b200_sample_f32(_p(logits), logits.stride(0), _p(temps), _p(seeds), vocab_offset, _p(idx), _p(out_val),
+                                 B, V, _stream()), "sample")
+    return idx
+
+
 def gather_rows(x, rows, out=None):
     _req(x, torch.bfloat16, "x"); _req(rows, torch.int32, "rows")
     n, H = rows.shape[0], x.shape[1]

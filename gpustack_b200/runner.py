@@ -118,7 +118,7 @@ class ModelRunner:
         self.cos_sin = self._cos_sin_cache().to(dev)
         # one int32 staging area for all step inputs (host pinned + device mirror)
         n_tiles_max = T // self.prefill_tile + self.max_seqs + 1
-        self.stage_words = _align(3 * T) + 5 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
+        self.stage_words = _align(3 * T) + 9 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
             + self.max_seqs * self.max_blocks + 64
         self.stage_host = torch.zeros(self.stage_words, dtype=torch.int32, pin_memory=True)
         self.stage_np = self.stage_host.numpy()
@@ -127,7 +127,8 @@ class ModelRunner:
         # fixed decode layout inside the staging area
         S = self.max_seqs
         self.d_ids, self.d_pos, self.d_slots, self.d_lens = 0, S, 2 * S, 3 * S
-        self.d_bt = 4 * S
+        self.d_temp, self.d_seed = 4 * S, 5 * S          # in-kernel sampler: fp32 temperatures (bit patterns), uint32 seeds
+        self.d_bt = 6 * S
         self._attn_ws: Optional[torch.Tensor] = None
 
     def _cos_sin_cache(self) -> torch.Tensor:
@@ -349,23 +350,27 @@ class ModelRunner:
         self._row_parallel(self.act[:T], lw.down, T, nxt, w_scale=lw.down_scale)
         self.stats["kernel_launches"] += 4
 
-    def _sample(self, n: int, rows: Optional[torch.Tensor]) -> None:
-        """greedy token of n sequences into self.out_ids[:n]; rows = last-token row of each."""
+    def _sample(self, n: int, rows: Optional[torch.Tensor], temps: torch.Tensor, seeds: torch.Tensor) -> None:
+        """Next token of n sequences into self.out_ids[:n]; rows = last-token row of each.  temps [n]
+        fp32 / seeds [n] int32 drive the one-pass sampler: 0 = greedy, > 0 = Gumbel-max temperature
+        sampling (exact softmax(logits / T) draws at the cost of an argmax, inside the decode graph,
+        and -- the noise being keyed by the global vocabulary index -- valid across vocab shards)."""
         x = self.xn[:n] if rows is None else ops.gather_rows(self.xn, rows, out=self.x_last[:n])
         lg = self.logits[:n]
         ops.gemm(x, self.w.lm_head, out=lg, out_dtype=torch.float32)
         if self.tp == 1:
-            ops.argmax(lg, out_idx=self.out_ids[:n])
+            ops.sample(lg, temps, seeds, out_idx=self.out_ids[:n])
             self.stats["kernel_launches"] += 2 + (rows is not None)
             return
+        v0 = self.w.vocab_start
         if self.peer_argmax is not None:
-            # local (max, argmax) straight into peer-mapped arrays, then ONE kernel picks the global winner
+            # local (max key, argmax) straight into peer-mapped arrays, then ONE kernel picks the global winner
             pa = self.peer_argmax
-            ops.argmax(lg, out_idx=pa.idxs[:n], out_val=pa.vals[:n])
+            ops.sample(lg, temps, seeds, out_idx=pa.idxs[:n], out_val=pa.vals[:n], vocab_offset=v0)
             pa.select(self.out_ids, n)
             self.stats["kernel_launches"] += 3 + (rows is not None)
             return
-        ops.argmax(lg, out_idx=self.out_ids[:n], out_val=self.out_vals[:n])
+        ops.sample(lg, temps, seeds, out_idx=self.out_ids[:n], out_val=self.out_vals[:n], vocab_offset=v0)
         vals = torch.empty(self.tp, n, dtype=torch.float32, device=self.device)
         idxs = torch.empty(self.tp, n, dtype=torch.int32, device=self.device)
         torch.distributed.all_gather_into_tensor(vals, self.out_vals[:n].contiguous(), group=self.tp_group)
@@ -391,7 +396,7 @@ class ModelRunner:
                                   num_splits=splits, workspace=ws)
 
         self._layers(B, attn)
-        self._sample(B, None)
+        self._sample(B, None, sd[self.d_temp:self.d_temp + B].view(torch.float32), sd[self.d_seed:self.d_seed + B])
 
     def capture_graphs(self) -> None:
         if self.ecfg.enforce_eager:
@@ -416,8 +421,10 @@ class ModelRunner:
         self._buckets = sorted(self.graphs)
         self.stats["kernel_launches"] = 0
 
-    def decode(self, B: int, last_token: np.ndarray, num_computed: np.ndarray, block_table: np.ndarray) -> np.ndarray:
-        """One decode step for rows 0..B-1 of the scheduler's persistent batch."""
+    def decode(self, B: int, last_token: np.ndarray, num_computed: np.ndarray, block_table: np.ndarray,
+               temps: Optional[np.ndarray] = None, seeds: Optional[np.ndarray] = None) -> np.ndarray:
+        """One decode step for rows 0..B-1 of the scheduler's persistent batch.  temps (fp32) / seeds
+        (uint32, already mixed with the position) per row drive the in-kernel sampler; None = greedy."""
         S, bs = self.max_seqs, self.block_size
         Bp = B
         if self.graphs:
@@ -430,6 +437,12 @@ class ModelRunner:
         st[self.d_pos:self.d_pos + B] = pos
         st[self.d_slots:self.d_slots + B] = block_table[np.arange(B), pos // bs] * bs + pos % bs
         st[self.d_lens:self.d_lens + B] = pos + 1
+        if temps is None:
+            st[self.d_temp:self.d_temp + Bp] = 0
+        else:
+            st[self.d_temp:self.d_temp + B] = np.asarray(temps[:B], dtype=np.float32).view(np.int32)
+            st[self.d_seed:self.d_seed + B] = np.asarray(seeds[:B], dtype=np.uint32).view(np.int32)
+            st[self.d_temp + B:self.d_temp + Bp] = 0
         if Bp > B:   # padding rows: no cache write, zero-length attention
             st[self.d_ids + B:self.d_ids + Bp] = 0
             st[self.d_pos + B:self.d_pos + Bp] = 0
@@ -456,7 +469,8 @@ class ModelRunner:
 
     # ------------------------------------------------------------------------------ prefill
     def prefill(self, token_chunks: Sequence[Sequence[int]], starts: Sequence[int], block_tables: Sequence[Sequence[int]],
-                sample: Sequence[bool], decode=None) -> np.ndarray:
+                sample: Sequence[bool], decode=None, sample_temps: Optional[Sequence[float]] = None,
+                sample_seeds: Optional[Sequence[int]] = None) -> np.ndarray:
         """Runs one (chunked) prefill step.  token_chunks[s] are the ids of chunk s, which occupies
         positions [starts[s], starts[s]+len).  Returns the greedy token of every chunk with
         sample[s] == True, in order.
@@ -482,7 +496,9 @@ class ModelRunner:
         o_ts = o_rows + _align(S + Bd)
         o_tq = o_ts + _align(nt)
         o_dl = o_tq + _align(nt)              # decode rows: sequence lengths
-        o_bt = o_dl + _align(Bd)
+        o_st = o_dl + _align(Bd)              # sampler inputs of the sampled rows: temperatures, seeds
+        o_ss = o_st + _align(S + Bd)
+        o_bt = o_ss + _align(S + Bd)
         end = o_bt + (S + Bd) * self.max_blocks
         if end > self.stage_words:
             raise B200Error("step inputs exceed the staging buffer")
@@ -512,6 +528,10 @@ class ModelRunner:
             self.stats["decode_kv_tokens"] += int(dpos.sum()) + Bd
         ns = len(sample_rows)
         st[o_rows:o_rows + ns] = sample_rows
+        st[o_st:o_st + ns] = 0
+        if sample_temps is not None and ns:      # one entry per sampled row (prefill rows first, then the riders)
+            st[o_st:o_st + ns] = np.asarray(sample_temps, dtype=np.float32).view(np.int32)
+            st[o_ss:o_ss + ns] = np.asarray(sample_seeds, dtype=np.uint32).view(np.int32)
         st[o_ts:o_ts + nt] = tile_seq
         st[o_tq:o_tq + nt] = tile_q0
         st[o_bt:end] = bt.reshape(-1)
@@ -548,7 +568,7 @@ class ModelRunner:
         if ns == 0:
             torch.cuda.current_stream().synchronize()
             return np.zeros(0, dtype=np.int32)
-        self._sample(ns, sd[o_rows:o_rows + ns])
+        self._sample(ns, sd[o_rows:o_rows + ns], sd[o_st:o_st + ns].view(torch.float32), sd[o_ss:o_ss + ns])
         self.out_host[:ns].copy_(self.out_ids[:ns], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.out_host[:ns].numpy().copy()

@@ -34,6 +34,19 @@ class SamplingParams:
     seed: Optional[int] = None
 
 
+def kernel_temperature(p: "SamplingParams") -> float:
+    """Temperature handed to the in-kernel (Gumbel-max) sampler: plain temperature sampling is done
+    there; greedy rows and nucleus rows (top_p < 1: re-sampled on the host from the logits) get 0."""
+    return float(p.temperature) if (p.temperature > 0.0 and p.top_p >= 1.0) else 0.0
+
+
+def step_seeds(seeds, positions) -> np.ndarray:
+    """Noise stream of one sampling step: the request's 32-bit seed mixed with the position of the token
+    being sampled (same request + same position = same draw, whatever the batch composition)."""
+    s = np.asarray(seeds, dtype=np.uint64) * np.uint64(0x9E3779B1) + np.asarray(positions, dtype=np.uint64) * np.uint64(0x85EBCA77)
+    return (s & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
 @dataclass
 class Request:
     req_id: str
@@ -48,6 +61,7 @@ class Request:
     finished: bool = False
     finish_reason: Optional[str] = None
     num_preemptions: int = 0
+    sample_seed: int = 0           # 32-bit stream id of the in-kernel sampler (params.seed, else drawn at admission)
     digests: List[bytes] = field(default_factory=list)   # chained keys of the full KV blocks
     num_cached_tokens: int = 0     # prompt tokens served from the prefix cache at admission
 
@@ -126,6 +140,11 @@ class Scheduler:
         self.check_eos = np.zeros(S, dtype=bool)
         self.n_blocks = np.zeros(S, dtype=np.int32)
         self.block_table = np.zeros((S, self.max_blocks_per_seq), dtype=np.int32)
+        # in-kernel sampler inputs of the resident rows: temperature (0 = greedy; nucleus rows are left
+        # greedy here and re-sampled on the host) and the per-request noise stream
+        self.temperature = np.zeros(S, dtype=np.float32)
+        self.sample_seed = np.zeros(S, dtype=np.uint32)
+        self._seed_rng = np.random.RandomState(0x5EED)
         self.num_preemptions = 0
 
     # ------------------------------------------------------------------ queue side
@@ -136,6 +155,8 @@ class Scheduler:
         if total > self.max_model_len:
             raise ValueError(f"prompt ({len(req.prompt_ids)}) + max_tokens ({req.params.max_tokens}) "
                              f"exceeds max_model_len ({self.max_model_len})")
+        req.sample_seed = (int(req.params.seed) if req.params.seed is not None
+                           else int(self._seed_rng.randint(0, 2 ** 31))) & 0xFFFFFFFF
         self.waiting.append(req)
 
     def abort(self, req_id: str) -> bool:
@@ -291,6 +312,8 @@ class Scheduler:
         self.num_computed[i] = r.num_computed   # K/V tokens in the cache; `first_token` sits at this position
         self.remaining[i] = r.params.max_tokens - len(r.output_ids)
         self.check_eos[i] = not r.params.ignore_eos
+        self.temperature[i] = kernel_temperature(r.params)
+        self.sample_seed[i] = r.sample_seed
         nb = len(r.blocks)
         self.n_blocks[i] = nb
         self.block_table[i, :nb] = r.blocks
@@ -304,7 +327,8 @@ class Scheduler:
             m = self.rows[last]
             self.rows[i] = m
             m.row = i
-            for a in (self.last_token, self.num_computed, self.remaining, self.check_eos, self.n_blocks):
+            for a in (self.last_token, self.num_computed, self.remaining, self.check_eos, self.n_blocks,
+                      self.temperature, self.sample_seed):
                 a[i] = a[last]
             self.block_table[i] = self.block_table[last]
         self.rows.pop()

@@ -83,6 +83,13 @@ int b200_embedding(const int32_t* ids, const void* table, void* out, int T, int 
  * out_val[b] (optional) = that maximum. */
 int b200_argmax_f32(const float* logits, int64_t ld, int32_t* out_idx, float* out_val, int B, int V,
                     void* stream);
+/* Sampler, one pass over the logits: row b is greedy when temps[b] == 0 (or temps is NULL), otherwise an
+ * exact softmax(logits / temps[b]) sample by the Gumbel-max trick with the counter-based noise
+ * u = hash(seeds[b], vocab_offset + column) -- deterministic per (seed, position), and composable with
+ * vocabulary-parallel shards (the cross-rank (max, argmax) exchange of greedy picks the sample).
+ * out_val (optional): the winning key of each row. */
+int b200_sample_f32(const float* logits, int64_t ld, const float* temps, const uint32_t* seeds,
+                    int vocab_offset, int32_t* out_idx, float* out_val, int B, int V, void* stream);
 /* gather rows: out[i] = x[rows[i]]; x [*,H] bf16 (used to pick each sequence's last token). */
 int b200_gather_rows(const void* x, const int32_t* rows, void* out, int n, int H, void* stream);
 

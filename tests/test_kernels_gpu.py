@@ -176,6 +176,38 @@ def test_embedding_gather_argmax(ops):
         assert idx.tolist() == [int(torch.argmax(r)) if i else Vv // 2 for i, r in enumerate(lg)]
 
 
+def test_one_pass_sampler_is_greedy_at_t0_exact_softmax_above_and_shards_compose(ops):
+    """b200_sample_f32: temperature 0 rows == argmax (lowest index on ties); temperature T rows are
+    Gumbel-max draws whose empirical distribution matches softmax(logits / T); the draw is a pure
+    function of (seed, global vocabulary index), so two vocabulary shards combined by their winning
+    keys (what tp_argmax_select_kernel does across ranks) reproduce the unsharded token exactly."""
+    g = torch.Generator().manual_seed(5)
+    V, N = 384, 40000
+    logits = (torch.randn(V, generator=g) * 2.0)
+    logits[7] = logits[300] = logits.max() + 0.5          # a tie for greedy: index 7 must win
+    T = 0.8
+    rows = logits.repeat(N, 1).contiguous().cuda()
+    temps = torch.full((N,), T, device="cuda"); temps[:100] = 0.0
+    seeds = torch.arange(N, dtype=torch.int64).mul(2654435761).remainder(2 ** 31).to(torch.int32).cuda()
+    vals = torch.empty(N, device="cuda")
+    idx = ops.sample(rows, temps, seeds, out_val=vals).cpu()
+    assert idx[:100].tolist() == [7] * 100
+    again = ops.sample(rows, temps, seeds).cpu()
+    assert torch.equal(idx, again)                          # deterministic in (seed, row)
+    p = torch.softmax(logits.double() / T, dim=0)
+    freq = torch.bincount(idx[100:].long(), minlength=V).double() / (N - 100)
+    tv = 0.5 * float((freq - p).abs().sum())
+    assert tv < 0.05, tv                                    # sampling noise at N = 4e4, V = 384 is ~0.03
+    assert abs(float(freq[7]) - float(p[7])) < 0.01 and abs(float(freq[300]) - float(p[300])) < 0.01
+    # vocabulary-parallel composition: shard [0, 160) and [160, 384) with global offsets
+    i0, v0 = torch.empty(N, dtype=torch.int32, device="cuda"), torch.empty(N, device="cuda")
+    i1, v1 = torch.empty(N, dtype=torch.int32, device="cuda"), torch.empty(N, device="cuda")
+    ops.sample(rows[:, :160].contiguous(), temps, seeds, out_idx=i0, out_val=v0, vocab_offset=0)
+    ops.sample(rows[:, 160:].contiguous(), temps, seeds, out_idx=i1, out_val=v1, vocab_offset=160)
+    combined = torch.where(v1 > v0, i1 + 160, i0).cpu()
+    assert torch.equal(combined, idx)
+
+
 # ------------------------------------------------------------------------------------ GEMM
 GEMM_SHAPES = [
     # M, N, K, splits, f32

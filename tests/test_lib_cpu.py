@@ -42,7 +42,8 @@ def test_argument_validation_without_gpu():
     assert h.b200_gemm_suggest_splits(64, 4096, 14336) >= 1
     assert h.b200_gemm_pick_block_x(1, 1, 64) == 16 and h.b200_gemm_pick_block_x(300, 1, 64) == 256
     assert h.b200_attn_prefill_tile(32, 8) == 32 and h.b200_attn_prefill_tile(64, 8) == 16
-    assert h.b200_attn_decode_workspace_bytes(4, 32, 128, 8) == 4 * 32 * 8 * 130 * 4
+    # fp32 partial O + (m, l) per (row, split), preceded by the 256-byte-aligned arrival counters of the in-kernel merge
+    assert h.b200_attn_decode_workspace_bytes(4, 32, 128, 8) == 4 * 32 * 8 * 130 * 4 + 512
 
 
 def test_ops_refuse_cpu_tensors():

@@ -21,12 +21,13 @@ class FakeRunner:
     def __init__(self):
         self.calls = []
 
-    def decode(self, B, last, computed, table):
+    def decode(self, B, last, computed, table, temps=None, seeds=None):
         self.calls.append(("decode", int(B), np.asarray(last[:B]).tolist(), np.asarray(computed[:B]).tolist(),
                            np.asarray(table[:B]).tolist()))
+        self.sampler = (np.asarray(temps[:B], dtype=np.float32).tolist(), np.asarray(seeds[:B], dtype=np.uint32).tolist())
         return np.arange(B, dtype=np.int32)
 
-    def prefill(self, chunks, starts, tables, sample, decode=None):
+    def prefill(self, chunks, starts, tables, sample, decode=None, sample_temps=None, sample_seeds=None):
         call = ("prefill", [list(map(int, c)) for c in chunks], list(map(int, starts)),
                 [list(map(int, t)) for t in tables], [bool(s) for s in sample])
         if decode is not None:     # mixed step: decode rows ride along
@@ -58,7 +59,10 @@ def _worker(rank, port, q):
         for s in steps:
             if s[0] == "decode":
                 _, B, last, comp, tab = s
-                payload = np.concatenate([np.array(last), np.array(comp), np.array(tab).reshape(-1)]).astype(np.int32)
+                temps = np.array([0.0, 0.7, 1.5], dtype=np.float32)
+                seeds = np.array([1, 2 ** 31 + 5, 2 ** 32 - 1], dtype=np.uint32)
+                payload = np.concatenate([np.array(last), np.array(comp), temps.view(np.int32), seeds.view(np.int32),
+                                          np.array(tab).reshape(-1)]).astype(np.int32)
                 tp.bcast_step([E._KIND_DECODE, B], payload)
             elif s[0] == "mixed":
                 eng._bcast_prefill(s[1], s[2], s[3], s[4], (s[5], np.array(s[6]), np.array(s[7]), np.array(s[8])))
@@ -70,6 +74,7 @@ def _worker(rank, port, q):
         q.put(("rank0", dt >= 0.0))
     else:
         E.TPWorker(eng).serve_forever()
+        assert eng.runner.sampler == ([0.0, 0.699999988079071, 1.5], [1, 2 ** 31 + 5, 2 ** 32 - 1])   # bit-exact round trip
         q.put(("rank1", eng.runner.calls))
     dist.destroy_process_group()
 
