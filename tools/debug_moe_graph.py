@@ -75,10 +75,12 @@ if __name__ == "__main__":
         run(sys.argv[1])
         sys.exit(0)
     res = {}
-    late = str(ROOT / "gpustack_b200" / "csrc" / "libb200_late.so")      # python -m gpustack_b200.build --late
+    # the default build triggers dependents late (after griddepcontrol.wait); the early-trigger
+    # experiment is a separate library: python -m gpustack_b200.build --early
+    early = str(ROOT / "gpustack_b200" / "csrc" / "libb200_early.so")
     for mode, env in (("eager", {}), ("graph8-all-pdl", {"B200_PDL_OFF_CLASSES": "0"}),
-                      ("graph8-all-pdl-late-trigger", {"B200_PDL_OFF_CLASSES": "0", "B200_LIB": late}),
-                      ("dense-eager", {}), ("dense-graph8-late-trigger", {"B200_LIB": late})):
+                      ("graph8-all-pdl-early-trigger", {"B200_PDL_OFF_CLASSES": "0", "B200_LIB": early}),
+                      ("dense-eager", {}), ("dense-graph8-early-trigger", {"B200_LIB": early})):
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, __file__, mode], capture_output=True, text=True, env=e, timeout=300)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
