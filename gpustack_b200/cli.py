@@ -46,6 +46,10 @@ def build_parser() -> argparse.ArgumentParser:
                    help="prefill steps also carry one decode token per running sequence (unified token budget)")
     s.add_argument("--seed", type=int, default=0)
     s.add_argument("--quantization", "-q", default=None, choices=[None, "fp8"])
+    s.add_argument("--speculative-config", default=None,
+                   help='JSON as the GPUStack launcher composes it (gpustack/worker/backends/vllm.py:333-367), e.g. '
+                        '\'{"method": "ngram", "num_speculative_tokens": 3, "prompt_lookup_max": 4, '
+                        '"prompt_lookup_min": 2}\'; draft-model methods (eagle3, mtp) run without speculation')
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
     est = sub.add_parser("estimate", help="print the engine's exact VRAM requirement (GPUSTACK_MODEL_VRAM_CLAIM)")
@@ -70,8 +74,14 @@ def _free_port() -> int:
 
 def _engine_config(args, tp: int):
     from .config import EngineConfig
+    from .spec_decode import SpeculativeConfig
 
-    return EngineConfig(model=args.model, served_model_name=(args.served_model_name or [None])[0],
+    spec = SpeculativeConfig.parse(args.speculative_config)          # ValueError on malformed JSON
+    if spec is not None and not spec.supported:
+        log.warning("speculative method %r needs a draft model and is not implemented: serving WITHOUT speculation "
+                    "(results are unaffected, only latency)", spec.method)
+        spec = None
+    return EngineConfig(speculative_config=spec.to_dict() if spec is not None else None, model=args.model, served_model_name=(args.served_model_name or [None])[0],
                         max_model_len=args.max_model_len, tensor_parallel_size=tp,
                         gpu_memory_utilization=args.gpu_memory_utilization, max_num_seqs=args.max_num_seqs,
                         max_num_batched_tokens=args.max_num_batched_tokens,

@@ -256,9 +256,23 @@ class EngineConfig:
     enable_prefix_caching: bool = True        # reuse full KV blocks across requests (reference engine default)
     quantization: Optional[str] = None        # None | "fp8" (W8A8: online per-tensor weights, per-token activations)
     mixed_steps: bool = True                  # prefill steps also carry the running sequences' decode tokens
+    # --speculative-config as a dict ({"method": "ngram", "num_speculative_tokens": k, ...}), None = off
+    speculative_config: Optional[dict] = None
     seed: int = 0
     block_size: int = 16
     cuda_graph_sizes: list = field(default_factory=list)
+
+    def speculative(self):
+        """Parsed speculative config, None when speculation is off or the method needs a draft model."""
+        from .spec_decode import SpeculativeConfig
+
+        c = SpeculativeConfig.parse(self.speculative_config)
+        return c if (c is not None and c.supported) else None
+
+    @property
+    def num_speculative_tokens(self) -> int:
+        c = self.speculative()
+        return c.num_speculative_tokens if c is not None else 0
 
     def graph_buckets(self) -> list:
         if self.cuda_graph_sizes:

@@ -23,6 +23,15 @@
 // V is consumed as an MN-major B operand straight from its [token][d] page layout (no transpose).
 // Two CTAs share an SM (112 KB of shared memory, 256 TMEM columns each): one CTA's softmax / epilogue
 // overlaps the other's MMAs.  Work per launch: 4 * T * ctx/2 * Hq * D FLOP (tensor-bound).
+//
+// PERSISTENT tile loop: the grid is 2 CTAs per SM and CTA c walks the work items c, c + grid, ...
+// of the (heaviest-first) list of (tile, kv-head) pairs.  Barriers, tensor memory and the K/V ring
+// live for the whole kernel; all mbarrier phases are running counters.  While a tile finishes (last
+// softmax block, PV, epilogue) the producer is already streaming the next tile's K/V into the ring
+// and -- once the last QK^T of the tile has retired (q_empty) -- its Q; every role loads the NEXT
+// item's metadata while it works on the current one.  The per-tile cost of a fresh CTA (barrier
+// init, TMEM allocation, three dependent metadata loads, cold Q/K latency, teardown) is paid once
+// per CTA instead of once per tile.  B200_ATTN_PERSIST=0 launches one CTA per work item instead.
 #include "common.cuh"
 #include "runtime.h"
 #include "../../include/b200.h"
@@ -64,7 +73,7 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                              const int32_t* __restrict__ block_table, int max_blocks,
                              const int32_t* __restrict__ cu_q, const int32_t* __restrict__ ctx_lens,
                              const int32_t* __restrict__ tile_seq, const int32_t* __restrict__ tile_q0,
-                             bf16* __restrict__ out, int Hq, int Hkv, float scale_log2) {
+                             int num_tiles, bf16* __restrict__ out, int Hq, int Hkv, float scale_log2) {
   constexpr int TPT = 128 / G;   // query tokens per tile
   extern __shared__ uint8_t fa_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) &
@@ -78,7 +87,9 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* p_full = bars + 11;
   uint64_t* p_empty = bars + 12;
   uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_empty = bars + 14;    // the tile's last Q K^T has retired: the Q buffer may be reloaded
+  uint64_t* o_empty = bars + 15;    // the epilogue has read O out of tensor memory (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,6 +109,8 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
     mbar_init(p_full, 4);     // one arrive per softmax warp
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_empty, 4);
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -110,62 +123,89 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // Q, the KV cache and the index buffers were written by preceding kernels / copies
 
-  const int tile = blockIdx.x, kvh = blockIdx.y;
-  const int seq = tile_seq[tile], q0 = tile_q0[tile];
-  const int q_begin = cu_q[seq];
-  const int q_len = cu_q[seq + 1] - q_begin;
-  const int ctx = ctx_lens[seq];
-  const int total_len = ctx + q_len;
-  const int kv_end = min(total_len, ctx + q0 + TPT);       // causal horizon of the tile (exclusive)
-  const int n_blocks = (kv_end + kFaKv - 1) / kFaKv;       // >= 1
-  const int n_pages_seq = (total_len + kFaPage - 1) / kFaPage;
+  // one work item = (tile, kv-head); tiles are listed heaviest first, the kv-heads of a tile are adjacent
+  struct Work {
+    int seq, kvh, q0, q_begin, q_len, ctx, total_len, n_blocks, n_pages_seq;
+  };
+  const int total_work = num_tiles * Hkv;
+  auto load_work = [&](int w) {
+    Work m;
+    if (w >= total_work) w = total_work - 1;               // prefetch past the end: harmless re-read
+    const int tile = w / Hkv;
+    m.kvh = w - tile * Hkv;
+    m.seq = __ldg(tile_seq + tile);
+    m.q0 = __ldg(tile_q0 + tile);
+    m.q_begin = __ldg(cu_q + m.seq);
+    m.q_len = __ldg(cu_q + m.seq + 1) - m.q_begin;
+    m.ctx = __ldg(ctx_lens + m.seq);
+    m.total_len = m.ctx + m.q_len;
+    const int kv_end = min(m.total_len, m.ctx + m.q0 + TPT);   // causal horizon of the tile (exclusive)
+    m.n_blocks = (kv_end + kFaKv - 1) / kFaKv;                 // >= 1
+    m.n_pages_seq = (m.total_len + kFaPage - 1) / kFaPage;
+    return m;
+  };
+  // Static schedule over the heaviest-first list: round r hands work r * P + c to CTA c on even rounds and
+  // r * P + (P - 1 - c) on odd ones (boustrophedon), so a CTA that got the heaviest item of one round
+  // gets the lightest of the next -- per-CTA sums stay level although causal tiles differ by up to
+  // ctx / 64 blocks.  (Plain c, c + P, c + 2P ... left a 29 % spread on one 8192-token prompt.)
+  const int n_cta = gridDim.x;
+  const int n_rounds = (total_work + n_cta - 1) / n_cta;
+  auto work_of = [&](int rd) { return rd * n_cta + ((rd & 1) ? (n_cta - 1 - (int)blockIdx.x) : (int)blockIdx.x); };
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the block table (lane l holds the page id of page base + l, one coalesced
     // load per 32 pages = 8 KV blocks; a dependent global load per TMA would serialise the ring at
     // L2 latency); lane 0 waits for the slot and issues the copies.
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kFaQBytes);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem + h * kFaQHalfBytes + g * TPT * 128, &tmap_q, q_full, (kvh * G + g) * kFaD + h * 64,
-                      q_begin + q0, kEvictFirst);
-      }
-    }
-    const int32_t* bt = block_table + (size_t)seq * max_blocks;
     constexpr int PPB = kFaKv / kFaPage;   // pages per KV block
     int slot = 0;
-    uint32_t phase = 0;
-    int my_blk = 0;
-    for (int j = 0; j < n_blocks; ++j) {
-      if ((j & 7) == 0) {   // refill: pages [j*4, j*4 + 32)
-        const int page = j * PPB + lane;
-        my_blk = page < n_pages_seq ? __ldg(bt + page) : 0;   // block 0: the all-zero null block
-      }
-      int rows[PPB];
-#pragma unroll
-      for (int p = 0; p < PPB; ++p)
-        rows[p] = (__shfl_sync(0xffffffffu, my_blk, ((j & 7) * PPB + p)) * Hkv + kvh) * kFaPage;
+    uint32_t phase = 0, it = 0;
+    Work nxt = load_work(work_of(0));
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const Work m = nxt;
+      nxt = load_work(work_of(rd + 1));     // in flight while this tile streams
+      if (work_of(rd) >= total_work) break; // only in the last, partial round
       if (lane == 0) {
+        if (it > 0) mbar_wait_guarded(q_empty, (it - 1) & 1);   // previous tile's Q K^T all retired
+        mbar_expect_tx(q_full, kFaQBytes);
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {   // K_j then V_j
-          mbar_wait_guarded(&kv_empty[slot], phase ^ 1);
-          mbar_expect_tx(&kv_full[slot], kFaSlotBytes);
-          uint8_t* dst = smem + kFaOffKV + slot * kFaSlotBytes;
+        for (int g = 0; g < G; ++g) {
 #pragma unroll
-          for (int p = 0; p < PPB; ++p) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d(dst + h * kFaHalfBytes + p * (kFaPage * 128), kv ? &tmap_v : &tmap_k, &kv_full[slot],
-                          h * 64, rows[p], kEvictNormal);
-          }
-          if (++slot == kFaSlots) { slot = 0; phase ^= 1; }
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem + h * kFaQHalfBytes + g * TPT * 128, &tmap_q, q_full, (m.kvh * G + g) * kFaD + h * 64,
+                        m.q_begin + m.q0, kEvictFirst);
         }
       }
-      __syncwarp();
+      const int32_t* bt = block_table + (size_t)m.seq * max_blocks;
+      int my_blk = 0;
+      for (int j = 0; j < m.n_blocks; ++j) {
+        if ((j & 7) == 0) {   // refill: pages [j*4, j*4 + 32)
+          const int page = j * PPB + lane;
+          my_blk = page < m.n_pages_seq ? __ldg(bt + page) : 0;   // block 0: the all-zero null block
+        }
+        int rows[PPB];
+#pragma unroll
+        for (int p = 0; p < PPB; ++p)
+          rows[p] = (__shfl_sync(0xffffffffu, my_blk, ((j & 7) * PPB + p)) * Hkv + m.kvh) * kFaPage;
+        if (lane == 0) {
+#pragma unroll
+          for (int kv = 0; kv < 2; ++kv) {   // K_j then V_j
+            mbar_wait_guarded(&kv_empty[slot], phase ^ 1);
+            mbar_expect_tx(&kv_full[slot], kFaSlotBytes);
+            uint8_t* dst = smem + kFaOffKV + slot * kFaSlotBytes;
+#pragma unroll
+            for (int p = 0; p < PPB; ++p) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                tma_load_2d(dst + h * kFaHalfBytes + p * (kFaPage * 128), kv ? &tmap_v : &tmap_k, &kv_full[slot],
+                            h * 64, rows[p], kEvictNormal);
+            }
+            if (++slot == kFaSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+        __syncwarp();
+      }
+      ++it;
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
@@ -175,161 +215,209 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const uint32_t q_addr = smem_u32(smem);
       const uint32_t kv_addr = smem_u32(smem + kFaOffKV);
       const uint32_t p_addr = smem_u32(smem + kFaOffP);
-      mbar_wait_guarded(q_full, 0);
-      tc_fence_after();
-      auto issue_s = [&](int j) {
-        const int slot = (2 * j) & 3;
-        mbar_wait_guarded(&kv_full[slot], ((2 * j) >> 2) & 1);
+      // gb: running KV-block counter of this CTA (across tiles).  Block gb uses S buffer gb & 1, ring
+      // slots 2gb (K) and 2gb + 1 (V), and the gb-th phase of p_full / p_empty.
+      auto issue_s = [&](uint32_t gb) {
+        const uint32_t slot = (2 * gb) & 3;
+        mbar_wait_guarded(&kv_full[slot], ((2 * gb) >> 2) & 1);
         tc_fence_after();
         const uint32_t k_addr = kv_addr + slot * kFaSlotBytes;
-        const uint32_t d = tmem_base + (uint32_t)((j & 1) * kFaKv);
+        const uint32_t d = tmem_base + (gb & 1) * kFaKv;
 #pragma unroll
         for (int k = 0; k < kFaD / kUmmaKBf16; ++k) {   // 8 MMAs x 16 head-dim elements
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           umma_bf16(d, umma_desc_k_sw128(q_addr + half * kFaQHalfBytes + off),
                     umma_desc_k_sw128(k_addr + half * kFaHalfBytes + off), idesc_s, k != 0);
         }
-        umma_commit(&kv_empty[slot]);     // K_j slot reusable once these MMAs retire
-        umma_commit(&s_full[j & 1]);      // S_j ready for the softmax warps
+        umma_commit(&kv_empty[slot]);     // K slot reusable once these MMAs retire
+        umma_commit(&s_full[gb & 1]);     // S ready for the softmax warps
       };
-      issue_s(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        // S buffer (j+1)&1 held S_{j-1}, which the softmax warps finished reading before p_full(j-1)
-        if (j + 1 < n_blocks) issue_s(j + 1);
-        mbar_wait_guarded(p_full, j & 1);
+      uint32_t gb = 0, it = 0;
+      Work nxt = load_work(work_of(0));
+      for (int rd = 0; rd < n_rounds; ++rd) {
+        const int n_blocks = nxt.n_blocks;
+        nxt = load_work(work_of(rd + 1));
+        if (work_of(rd) >= total_work) break;
+        mbar_wait_guarded(q_full, it & 1);
         tc_fence_after();
-        const int slot = (2 * j + 1) & 3;
-        mbar_wait_guarded(&kv_full[slot], ((2 * j + 1) >> 2) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = kv_addr + slot * kFaSlotBytes;
+        issue_s(gb);
+        if (n_blocks == 1) umma_commit(q_empty);
+        for (int j = 0; j < n_blocks; ++j, ++gb) {
+          // S buffer (gb+1)&1 held S_{gb-1}, which the softmax warps finished reading before p_full(gb-1)
+          if (j + 1 < n_blocks) {
+            issue_s(gb + 1);
+            if (j + 2 == n_blocks) umma_commit(q_empty);   // the tile's last Q K^T: Q may be reloaded
+          }
+          mbar_wait_guarded(p_full, gb & 1);
+          tc_fence_after();
+          if (j == 0 && it > 0) {           // PV_0 overwrites O: the previous tile's epilogue must have read it
+            mbar_wait_guarded(o_empty, (it - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t slot = (2 * gb + 1) & 3;
+          mbar_wait_guarded(&kv_full[slot], ((2 * gb + 1) >> 2) & 1);
+          tc_fence_after();
+          const uint32_t v_addr = kv_addr + slot * kFaSlotBytes;
 #pragma unroll
-        for (int k = 0; k < kFaKv / kUmmaKBf16; ++k) {   // 4 MMAs x 16 KV tokens
-          const uint64_t v_desc = umma_desc_mn_sw128(v_addr + k * (kUmmaKBf16 * 128), kFaHalfBytes, 1024);
-          if constexpr (P_TMEM)   // A = P_j in TMEM: 16 bf16 of K = 8 columns per MMA
-            umma_bf16_ts(tmem_base + 2 * kFaKv, tmem_base + (uint32_t)((j & 1) * kFaKv + k * 8), v_desc, idesc_o,
-                         (j | k) != 0);
-          else
-            umma_bf16(tmem_base + 2 * kFaKv, umma_desc_k_sw128(p_addr + k * 32), v_desc, idesc_o, (j | k) != 0);
+          for (int k = 0; k < kFaKv / kUmmaKBf16; ++k) {   // 4 MMAs x 16 KV tokens
+            const uint64_t v_desc = umma_desc_mn_sw128(v_addr + k * (kUmmaKBf16 * 128), kFaHalfBytes, 1024);
+            if constexpr (P_TMEM)   // A = P in TMEM: 16 bf16 of K = 8 columns per MMA
+              umma_bf16_ts(tmem_base + 2 * kFaKv, tmem_base + (gb & 1) * kFaKv + k * 8, v_desc, idesc_o,
+                           (j | k) != 0);
+            else
+              umma_bf16(tmem_base + 2 * kFaKv, umma_desc_k_sw128(p_addr + k * 32), v_desc, idesc_o, (j | k) != 0);
+          }
+          umma_commit(&kv_empty[slot]);     // V slot reusable
+          umma_commit(p_empty);             // P buffer and the O accumulator are stable again
         }
-        umma_commit(&kv_empty[slot]);     // V_j slot reusable
-        umma_commit(p_empty);             // P buffer and the O accumulator are stable again
+        umma_commit(o_full);
+        ++it;
       }
-      umma_commit(o_full);
     }
   } else {
     // ------------------------------------------------------------------ softmax / epilogue (warps 0..3)
     const int row = warp * 32 + lane;        // TMEM lane = tile row = (head g, token tok)
     const int g = row / TPT, tok = row % TPT;
-    const int qi = q0 + tok;
-    const bool valid = qi < q_len;
-    const int qpos = ctx + qi;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t p_row = smem_u32(smem + kFaOffP) + (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
-    float m_used = -INFINITY, l = 0.f;
+    const bool wide = (reinterpret_cast<uintptr_t>(out) & 31u) == 0;   // 256-bit stores: one full sector per thread
+    uint32_t gb = 0, it = 0;
+    Work nxt = load_work(work_of(0));
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const Work m = nxt;
+      nxt = load_work(work_of(rd + 1));
+      if (work_of(rd) >= total_work) break;
+      const int qi = m.q0 + tok;
+      const bool valid = qi < m.q_len;
+      const int qpos = m.ctx + qi;
+      const int total_len = m.total_len;
+      float m_used = -INFINITY, l = 0.f;
 
-    for (int j = 0; j < n_blocks; ++j) {
-      mbar_wait_guarded(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32(t_lane + (uint32_t)((j & 1) * kFaKv), s0);
-      tmem_ld_32x32(t_lane + (uint32_t)((j & 1) * kFaKv + 32), s1);
-      tmem_ld_wait();
-      const int kv0 = j * kFaKv;
-      // block-uniform: does any row of the tile see a masked column in this block?
-      const bool need_mask = (kv0 + kFaKv - 1 > ctx + q0) || (kv0 + kFaKv - 1 >= total_len);
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float a = __uint_as_float(s0[c]) * scale_log2;
-        float b = __uint_as_float(s1[c]) * scale_log2;
-        if (need_mask) {
-          const int ka = kv0 + c, kb = kv0 + 32 + c;
-          if (ka > qpos || ka >= total_len) a = -INFINITY;
-          if (kb > qpos || kb >= total_len) b = -INFINITY;
-        }
-        s0[c] = __float_as_uint(a);
-        s1[c] = __float_as_uint(b);
-        mx = fmaxf(mx, fmaxf(a, b));
-      }
-      // lazy rescale: move the reference maximum only when the row maximum outgrew it by > 2^8
-      // (always on the first block, where m_used = -inf and the factor is exp2(-inf) = 0)
-      float alpha = 1.f;
-      bool rescale = false;
-      if (mx > m_used + kFaRescaleThreshold) {
-        alpha = ex2_approx(m_used - mx);
-        m_used = mx;
-        l *= alpha;
-        rescale = j > 0;
-      }
-      uint32_t pk[32];
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const float p0 = ex2_approx(__uint_as_float(s0[c]) - m_used);
-        const float p1 = ex2_approx(__uint_as_float(s0[c + 1]) - m_used);
-        const float p2 = ex2_approx(__uint_as_float(s1[c]) - m_used);
-        const float p3 = ex2_approx(__uint_as_float(s1[c + 1]) - m_used);
-        sum += (p0 + p1) + (p2 + p3);
-        pk[c >> 1] = pack_bf16(p0, p1);
-        pk[16 + (c >> 1)] = pack_bf16(p2, p3);
-      }
-      l += sum;
-      const bool any_rescale = __any_sync(0xffffffffu, rescale);
-      if (j > 0 && (!P_TMEM || any_rescale)) {   // PV_{j-1} has retired: smem P may be overwritten, O may be rescaled
-        mbar_wait_guarded(p_empty, (j - 1) & 1);
+      for (int j = 0; j < m.n_blocks; ++j, ++gb) {
+        const uint32_t s_col = (gb & 1) * kFaKv;
+        mbar_wait_guarded(&s_full[gb & 1], (gb >> 1) & 1);
         tc_fence_after();
-      }
-      if (any_rescale) {
-#pragma unroll 1
-        for (int c4 = 0; c4 < kFaD / 32; ++c4) {
-          uint32_t o[32];
-          tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
-          tmem_ld_wait();
+        uint32_t s0[32], s1[32];
+        tmem_ld_32x32(t_lane + s_col, s0);
+        tmem_ld_32x32(t_lane + s_col + 32, s1);
+        tmem_ld_wait();
+        const int kv0 = j * kFaKv;
+        // block-uniform: does any row of the tile see a masked column in this block?
+        const bool need_mask = (kv0 + kFaKv - 1 > m.ctx + m.q0) || (kv0 + kFaKv - 1 >= total_len);
+        if (need_mask) {   // ONE warp-uniform branch per block (the condition is tile-uniform), not one per column
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+          for (int c = 0; c < 32; ++c) {
+            const int ka = kv0 + c, kb = kv0 + 32 + c;
+            if (ka > qpos || ka >= total_len) s0[c] = 0xff800000u;   // -inf
+            if (kb > qpos || kb >= total_len) s1[c] = 0xff800000u;
+          }
         }
-        tmem_st_wait();
-      }
-      if constexpr (P_TMEM) {
-        // P row (64 bf16 = 32 packed columns) over the first half of the S_j buffer this thread just read
-        tmem_st_32x32(t_lane + (uint32_t)((j & 1) * kFaKv), pk);
-        tmem_st_wait();
-      } else {
-        // P row (64 bf16 = 8 chunks of 16 B) into the 128B-swizzled K-major A-operand layout
+        // row maximum on the raw scores (scale > 0 commutes with max); the scale itself is folded
+        // into the exponent's FFMA below
+        float mx = -INFINITY;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          st_shared_v4(p_row + (((uint32_t)ch ^ sw) << 4),
-                       make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-
-    // ---- epilogue: O / l -> bf16 -> out[token, head, :]
-    mbar_wait_guarded(o_full, 0);
-    tc_fence_after();
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    bf16* orow = out + ((size_t)(q_begin + qi) * Hq + (size_t)(kvh * G + g)) * kFaD;
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+        mx *= scale_log2;
+        // lazy rescale: move the reference maximum only when the row maximum outgrew it by > 2^8
+        // (always on the first block, where m_used = -inf and the factor is exp2(-inf) = 0)
+        float alpha = 1.f;
+        bool rescale = false;
+        if (mx > m_used + kFaRescaleThreshold) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          l *= alpha;
+          rescale = j > 0;
+        }
+        uint32_t pk[32];
+        float sum = 0.f;
+        const float neg_m = -m_used;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s0[c]), scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s0[c + 1]), scale_log2, neg_m));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(s1[c]), scale_log2, neg_m));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(s1[c + 1]), scale_log2, neg_m));
+          sum += (p0 + p1) + (p2 + p3);
+          pk[c >> 1] = pack_bf16(p0, p1);
+          pk[16 + (c >> 1)] = pack_bf16(p2, p3);
+        }
+        l += sum;
+        const bool any_rescale = __any_sync(0xffffffffu, rescale);
+        // the previous block's PV (possibly the previous tile's last) must have retired before the
+        // shared-memory P buffer is overwritten / before O is rescaled (any_rescale implies j > 0)
+        if ((j > 0 || it > 0) && (!P_TMEM || any_rescale)) {
+          mbar_wait_guarded(p_empty, (gb - 1) & 1);
+          tc_fence_after();
+        }
+        if (any_rescale) {
 #pragma unroll 1
-    for (int c4 = 0; c4 < kFaD / 32; ++c4) {
-      uint32_t o[32];
-      tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
-      tmem_ld_wait();
-      if (valid) {
+          for (int c4 = 0; c4 < kFaD / 32; ++c4) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o);
+          }
+          tmem_st_wait();
+        }
+        if constexpr (P_TMEM) {
+          // P row (64 bf16 = 32 packed columns) over the first half of the S buffer this thread just read
+          tmem_st_32x32(t_lane + s_col, pk);
+          tmem_st_wait();
+        } else {
+          // P row (64 bf16 = 8 chunks of 16 B) into the 128B-swizzled K-major A-operand layout
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            st_shared_v4(p_row + (((uint32_t)ch ^ sw) << 4),
+                         make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> out[token, head, :]
+      mbar_wait_guarded(o_full, it & 1);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = out + ((size_t)(m.q_begin + qi) * Hq + (size_t)(m.kvh * G + g)) * kFaD;
+      auto store32 = [&](const uint32_t (&o)[32], bf16* dst) {            // 32 fp32 columns -> 64 bytes of the row
+        uint4 wv[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[8 * v + 0]) * inv, __uint_as_float(o[8 * v + 1]) * inv);
-          w.y = pack_bf16(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv);
-          w.z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv);
-          w.w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv);
-          st_v4(orow + c4 * 32 + v * 8, w);
+          wv[v].x = pack_bf16(__uint_as_float(o[8 * v + 0]) * inv, __uint_as_float(o[8 * v + 1]) * inv);
+          wv[v].y = pack_bf16(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv);
+          wv[v].z = pack_bf16(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv);
+          wv[v].w = pack_bf16(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv);
+        }
+        if (wide) {
+          st_v8(dst, wv[0], wv[1]);
+          st_v8(dst + 16, wv[2], wv[3]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) st_v4(dst + v * 8, wv[v]);
+        }
+      };
+#pragma unroll 1
+      for (int c4 = 0; c4 < kFaD / 32; c4 += 2) {   // two TMEM loads in flight per wait
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32), o0);
+        tmem_ld_32x32(t_lane + (uint32_t)(2 * kFaKv + c4 * 32 + 32), o1);
+        tmem_ld_wait();
+        if (c4 + 2 >= kFaD / 32) {   // O is in registers: the next tile's first PV may overwrite the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+        }
+        if (valid) {
+          store32(o0, orow + c4 * 32);
+          store32(o1, orow + c4 * 32 + 32);
         }
       }
+      ++it;
     }
   }
 
@@ -368,9 +456,17 @@ static int launch_prefill_tc(const void* q, int64_t q_stride, int num_tokens, co
   rc = make_tmap_bf16_2d(&tv, v_cache, kv_rows, kFaD, kFaD, kFaPage, 64);
   if (rc) return rc;
   const float scale_log2 = scale * 1.4426950408889634f;
-  cudaError_t e = launch_pdl(kernel, dim3(num_tiles, Hkv), dim3(kFaThreads), (size_t)kFaSmemBytes, stream, 1, tq, tk,
-                             tv, block_table, max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, (bf16*)out, Hq, Hkv,
-                             scale_log2);
+  static int persist = -1;
+  if (persist < 0) {
+    const char* pe = getenv("B200_ATTN_PERSIST");   // =0: one CTA per (tile, kv-head) instead of the persistent loop
+    persist = (pe && pe[0] == '0') ? 0 : 1;
+  }
+  const long long total_work = (long long)num_tiles * Hkv;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int grid = (int)(persist ? (total_work < 2LL * sms ? total_work : 2LL * sms) : total_work);
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(kFaThreads), (size_t)kFaSmemBytes, stream, 1, tq, tk, tv,
+                             block_table, max_blocks, cu_q, ctx_lens, tile_seq, tile_q0, num_tiles, (bf16*)out, Hq,
+                             Hkv, scale_log2);
   if (e != cudaSuccess) {
     b200_set_error("b200_paged_attn_prefill(tc): launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -92,6 +92,12 @@ __device__ __forceinline__ uint4 ld_v4(const void* p) {
 __device__ __forceinline__ void st_v4(void* p, const uint4& v) {
   *reinterpret_cast<uint4*>(p) = v;
 }
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per thread; p must be 32-byte aligned
+__device__ __forceinline__ void st_v8(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
 __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)

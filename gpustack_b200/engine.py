@@ -19,7 +19,7 @@ import torch
 from .config import EngineConfig, ModelConfig
 from .lib import B200Error
 from .runner import ModelRunner
-from .scheduler import (DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, StepOutput,
+from .scheduler import (DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, SpecPlan, StepOutput,
                         kernel_temperature, step_seeds)
 from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, random_state_dict,
                       shard_state_dict)
@@ -203,7 +203,8 @@ class LLMEngine:
         self.runner.capture_graphs()
         self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
                                ecfg.max_model_len, mcfg.eos_token_ids or mcfg.eos_token_id, ecfg.enable_prefix_caching,
-                               mixed_steps=ecfg.mixed_steps)
+                               mixed_steps=ecfg.mixed_steps, speculative=ecfg.speculative(),
+                               max_sample_rows=self.runner.max_sample)
         self.requests: Dict[str, Request] = {}
         self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
         self.step_time = {"prefill": 0.0, "decode": 0.0}
@@ -284,6 +285,25 @@ class LLMEngine:
             toks = self.runner.decode(B, s.last_token, s.num_computed, s.block_table, temps, seeds)
             toks = self._apply_sampling(list(s.rows[:B]), toks)
             out = s.update_decode(plan, toks)
+            self.step_time["decode"] += time.perf_counter() - t0
+        elif isinstance(plan, SpecPlan):
+            # speculative verification: row i runs [last_token, drafts...] at positions num_computed[i]..
+            # through the chunked-prefill path, every row of every chunk is sampled (spec_decode.py)
+            s = self.sched
+            B = plan.batch
+            chunks = [[int(s.last_token[i])] + plan.drafts[i] for i in range(B)]
+            starts = [int(x) for x in s.num_computed[:B]]
+            tables = [s.rows[i].blocks for i in range(B)]
+            counts = [len(c) for c in chunks]
+            stemps = np.repeat(s.temperature[:B], counts).astype(np.float32)
+            pos = np.concatenate([np.arange(st, st + n) for st, n in zip(starts, counts)])
+            sseeds = step_seeds(np.repeat(s.sample_seed[:B], counts), pos)
+            if self.tp:
+                self._bcast_prefill(chunks, starts, tables, counts, None, stemps, sseeds)
+            toks = self.runner.prefill(chunks, starts, tables, counts, sample_temps=stemps, sample_seeds=sseeds)
+            # nucleus rows never carry drafts (one sampled row each): re-sampled on the host like in a decode step
+            toks = self._apply_sampling([s.rows[i] for i in range(B) for _ in range(counts[i])], toks)
+            out = s.update_spec(plan, toks)
             self.step_time["decode"] += time.perf_counter() - t0
         else:
             mixed = isinstance(plan, MixedPlan)
@@ -451,5 +471,5 @@ class TPWorker:
                 ns = h[3]
                 st_ = p[off:off + ns].view(np.float32) if ns else None
                 ss_ = p[off + ns:off + 2 * ns].view(np.uint32) if ns else None
-                run.prefill(chunks, starts.tolist(), tables, [bool(x) for x in sample], decode=dec, sample_temps=st_,
+                run.prefill(chunks, starts.tolist(), tables, [int(x) for x in sample], decode=dec, sample_temps=st_,
                             sample_seeds=ss_)

@@ -74,12 +74,13 @@ def workspace_bytes_per_gpu(m: ModelConfig, e: EngineConfig, tp: int, quantizati
     hq, hkv, D = m.num_attention_heads // tp, m.num_key_value_heads // tp, m.head_dim
     qkv_w = (hq + 2 * hkv) * D
     v_local = math.ceil(m.vocab_size / tp)
-    act = T * (3 * H + qkv_w + hq * D + I) * 2 + S * H * 2
-    logits = S * v_local * 4
+    S_smp = min(T, S * (1 + e.num_speculative_tokens))       # rows one step may sample (runner.max_sample)
+    act = T * (3 * H + qkv_w + hq * D + I) * 2 + S_smp * H * 2
+    logits = S_smp * v_local * 4
     partials = max(8 * min(256, T) * max(H, qkv_w), T * qkv_w if m.attention_bias else 0) * 4
     max_len = e.max_model_len or m.max_position_embeddings
     rope = max_len * D * 2
-    staging = (3 * T + 4 * S + S * math.ceil(max_len / e.block_size) + 2 * T) * 4
+    staging = (3 * T + 6 * S + 3 * S_smp + S * math.ceil(max_len / e.block_size) + 2 * T) * 4
     extra = 0
     if (quantization or m.quantization) == "fp8":
         extra += T * max(H, hq * D, I) + T * 4

@@ -56,6 +56,9 @@ class ModelRunner:
         self.max_blocks = (self.max_model_len + self.block_size - 1) // self.block_size
         self.max_seqs = ecfg.max_num_seqs
         self.max_tokens = max(ecfg.max_num_batched_tokens, self.max_seqs)
+        # rows one step may sample: one per sequence, (1 + k) per sequence when speculative decoding
+        # verifies k drafts per step (spec_decode.py)
+        self.max_sample = min(self.max_tokens, self.max_seqs * (1 + ecfg.num_speculative_tokens))
         self.prefill_tile = ops.attn_prefill_tile(self.Hq, self.Hkv)
         self.v_local = weights.lm_head.shape[0]
         self.fp8 = weights.layers[0].qkv.dtype == ops.FP8
@@ -86,7 +89,7 @@ class ModelRunner:
             from .tp_comm import PeerArgmax
 
             per = (mcfg.vocab_size + self.tp - 1) // self.tp
-            self.peer_argmax = PeerArgmax(tp_ctx, self.max_seqs, per, self.device)
+            self.peer_argmax = PeerArgmax(tp_ctx, self.max_sample, per, self.device)
         self.stats = {"prefill_steps": 0, "decode_steps": 0, "graph_replays": 0, "kernel_launches": 0,
                       "h2d_bytes": 0, "d2h_bytes": 0, "decode_kv_tokens": 0, "prefill_tokens": 0}
         self.launches_per_decode = 0
@@ -108,22 +111,22 @@ class ModelRunner:
             kmax = max(H, self.Hq * self.D, self.I)
             self.xq = e(T * kmax, dt=ops.FP8)          # flat; viewed [T, K] per projection
             self.xs = e(T, dt=torch.float32)
-        self.x_last = e(self.max_seqs, H)
-        self.logits = e(self.max_seqs, self.v_local, dt=torch.float32)
-        self.out_ids = torch.zeros(self.max_seqs, dtype=torch.int32, device=dev)
-        self.out_vals = torch.zeros(self.max_seqs, dtype=torch.float32, device=dev)
+        self.x_last = e(self.max_sample, H)
+        self.logits = e(self.max_sample, self.v_local, dt=torch.float32)
+        self.out_ids = torch.zeros(self.max_sample, dtype=torch.int32, device=dev)
+        self.out_vals = torch.zeros(self.max_sample, dtype=torch.float32, device=dev)
         has_bias = self.w.layers[0].qkv_bias is not None
         n_part = max(8 * min(_SPLITK_MAX_M, T) * max(H, self.qkv_width), T * self.qkv_width if has_bias else 0)
         self.partials = e(n_part, dt=torch.float32)   # flat: [splits, T, W]
         self.cos_sin = self._cos_sin_cache().to(dev)
         # one int32 staging area for all step inputs (host pinned + device mirror)
         n_tiles_max = T // self.prefill_tile + self.max_seqs + 1
-        self.stage_words = _align(3 * T) + 9 * _align(self.max_seqs + 1) + 2 * _align(n_tiles_max) \
-            + self.max_seqs * self.max_blocks + 64
+        self.stage_words = 3 * _align(T) + 6 * _align(self.max_seqs + 1) + 3 * _align(self.max_sample + 1) \
+            + 2 * _align(n_tiles_max) + self.max_seqs * self.max_blocks + 64
         self.stage_host = torch.zeros(self.stage_words, dtype=torch.int32, pin_memory=True)
         self.stage_np = self.stage_host.numpy()
         self.stage_dev = torch.zeros(self.stage_words, dtype=torch.int32, device=dev)
-        self.out_host = torch.zeros(self.max_seqs, dtype=torch.int32, pin_memory=True)
+        self.out_host = torch.zeros(self.max_sample, dtype=torch.int32, pin_memory=True)
         # fixed decode layout inside the staging area
         S = self.max_seqs
         self.d_ids, self.d_pos, self.d_slots, self.d_lens = 0, S, 2 * S, 3 * S
@@ -472,8 +475,9 @@ class ModelRunner:
                 sample: Sequence[bool], decode=None, sample_temps: Optional[Sequence[float]] = None,
                 sample_seeds: Optional[Sequence[int]] = None) -> np.ndarray:
         """Runs one (chunked) prefill step.  token_chunks[s] are the ids of chunk s, which occupies
-        positions [starts[s], starts[s]+len).  Returns the greedy token of every chunk with
-        sample[s] == True, in order.
+        positions [starts[s], starts[s]+len).  sample[s] is the number of TRAILING rows of chunk s whose
+        next token is sampled (False/0: none, True/1: the last row = a completed prompt, 1 + k: every row
+        of a speculative verification chunk).  Returns the sampled tokens, chunk after chunk.
         decode = (B, last_token, num_computed, block_table) makes it a MIXED step: rows 0..B-1 of the
         scheduler's persistent batch ride along with one decode token each (appended after the
         prefill tokens: same GEMMs / norms / RoPE launches, the weights are streamed once for
@@ -488,17 +492,21 @@ class ModelRunner:
         bs = self.block_size
         st = self.stage_np
         o_ids, o_pos, o_slots = 0, _align(T), 2 * _align(T)
+        counts = [min(int(c), n) for c, n in zip(sample, lens)]     # bool -> 0 / 1
+        NS = sum(counts) + Bd
+        if NS > self.max_sample:
+            raise B200Error(f"prefill step samples {NS} rows, the logits buffer holds {self.max_sample}")
         o_cu = 3 * _align(T)
         o_ctx = o_cu + _align(S + 1)
         o_rows = o_ctx + _align(S)
         tile_seq, tile_q0 = ops.build_prefill_tiles(lens, self.prefill_tile, starts)
         nt = len(tile_seq)
-        o_ts = o_rows + _align(S + Bd)
+        o_ts = o_rows + _align(NS)
         o_tq = o_ts + _align(nt)
         o_dl = o_tq + _align(nt)              # decode rows: sequence lengths
         o_st = o_dl + _align(Bd)              # sampler inputs of the sampled rows: temperatures, seeds
-        o_ss = o_st + _align(S + Bd)
-        o_bt = o_ss + _align(S + Bd)
+        o_ss = o_st + _align(NS)
+        o_bt = o_ss + _align(NS)
         end = o_bt + (S + Bd) * self.max_blocks
         if end > self.stage_words:
             raise B200Error("step inputs exceed the staging buffer")
@@ -515,7 +523,7 @@ class ModelRunner:
             st[o_slots + a:o_slots + b] = tbl[p // bs] * bs + p % bs
         st[o_cu:o_cu + S + 1] = cu
         st[o_ctx:o_ctx + S] = starts
-        sample_rows = [int(cu[s + 1]) - 1 for s in range(S) if sample[s]]
+        sample_rows = [r for s in range(S) for r in range(int(cu[s + 1]) - counts[s], int(cu[s + 1]))]
         if Bd:
             _, last_token, num_computed, dbt = decode
             dpos = np.asarray(num_computed[:Bd], dtype=np.int32)

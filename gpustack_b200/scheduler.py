@@ -22,6 +22,7 @@ from typing import Deque, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .kv_cache import BlockPool, block_digests
+from .spec_decode import NgramIndex, SpeculativeConfig, verify
 
 
 @dataclass
@@ -104,6 +105,18 @@ class MixedPlan:
 
 
 @dataclass
+class SpecPlan:
+    """Speculative decode step: every resident row runs `[last_token, draft_1 .. draft_k]` (k may be 0)
+    through one forward; all rows of every chunk are sampled (spec_decode.py)."""
+    batch: int
+    drafts: List[List[int]]        # per row 0..batch-1
+
+    @property
+    def num_tokens(self) -> int:
+        return self.batch + sum(len(d) for d in self.drafts)
+
+
+@dataclass
 class StepOutput:
     req_ids: List[str]
     token_ids: List[int]
@@ -112,8 +125,11 @@ class StepOutput:
 
 class Scheduler:
     def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: int, eos_token_id, enable_prefix_caching: bool = False, mixed_steps: bool = True):
-        """eos_token_id: one id, an iterable of ids (every turn terminator of the checkpoint), or None."""
+                 max_model_len: int, eos_token_id, enable_prefix_caching: bool = False, mixed_steps: bool = True,
+                 speculative: Optional[SpeculativeConfig] = None, max_sample_rows: Optional[int] = None):
+        """eos_token_id: one id, an iterable of ids (every turn terminator of the checkpoint), or None.
+        speculative: n-gram speculative decoding on pure decode steps (spec_decode.py); max_sample_rows
+        bounds the rows one step may sample (the runner's logits buffer)."""
         self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching)
         self.block_size = block_size
         self.max_num_seqs = max_num_seqs
@@ -146,6 +162,10 @@ class Scheduler:
         self.sample_seed = np.zeros(S, dtype=np.uint32)
         self._seed_rng = np.random.RandomState(0x5EED)
         self.num_preemptions = 0
+        self.spec = speculative if (speculative is not None and speculative.supported) else None
+        self.max_sample_rows = max_sample_rows if max_sample_rows is not None else max_num_seqs
+        self.proposer = self._ngram_propose      # (request, k) -> draft token ids; tests substitute their own
+        self.spec_stats = {"steps": 0, "drafted": 0, "accepted": 0}
 
     # ------------------------------------------------------------------ queue side
     def add(self, req: Request) -> None:
@@ -226,8 +246,96 @@ class Scheduler:
         if self.rows:
             self._ensure_decode_blocks()
             if self.rows:
+                if self.spec is not None and len(self.rows) < self.spec.disable_by_batch_size:
+                    sp = self._schedule_spec()
+                    if sp is not None:
+                        return sp
                 return DecodePlan(batch=len(self.rows))
         return None
+
+    # ------------------------------------------------------------------ speculative decoding
+    def _ngram_propose(self, r: Request, k: int) -> List[int]:
+        idx = getattr(r, "_ngram", None)
+        n_ids = len(r.prompt_ids) + len(r.output_ids)
+        if idx is None:
+            idx = r._ngram = NgramIndex(self.spec.prompt_lookup_min, self.spec.prompt_lookup_max)
+        if len(idx.ids) > n_ids:
+            idx.truncate(0)
+        if len(idx.ids) < n_ids:
+            idx.extend(r.all_ids[len(idx.ids):])
+        return idx.propose(k)
+
+    def _schedule_spec(self) -> Optional[SpecPlan]:
+        """Drafts for the resident rows (rows already hold a block for position num_computed).  A draft
+        is cut to what the request may still emit, to the model length, to the step's token / sample-row
+        budgets and to the KV blocks that are free right now -- speculation never preempts."""
+        B = len(self.rows)
+        k_max = self.spec.num_speculative_tokens
+        tok_budget = min(self.max_tokens_per_step, self.max_sample_rows) - B
+        drafts: List[List[int]] = []
+        any_draft = False
+        for i, r in enumerate(self.rows):
+            d: List[int] = []
+            p = r.params
+            room = min(k_max, int(self.remaining[i]) - 1, tok_budget,
+                       self.max_model_len - 1 - int(self.num_computed[i]) - 1)
+            if room > 0 and not (p.temperature > 0.0 and p.top_p < 1.0):     # nucleus rows are sampled on the host
+                d = [int(t) for t in self.proposer(r, room)[:room]]
+            if d:
+                last_pos = int(self.num_computed[i]) + len(d)
+                need = last_pos // self.block_size + 1 - int(self.n_blocks[i])
+                if need > 0:
+                    if need > self.pool.num_free:
+                        d = d[:max(0, (int(self.n_blocks[i]) * self.block_size - 1) - int(self.num_computed[i]))]
+                    else:
+                        for b in self.pool.allocate(need):
+                            r.blocks.append(b)
+                            self.block_table[i, self.n_blocks[i]] = b
+                            self.n_blocks[i] += 1
+            tok_budget -= len(d)
+            any_draft |= bool(d)
+            drafts.append(d)
+        if not any_draft:
+            return None
+        return SpecPlan(B, drafts)
+
+    def update_spec(self, plan: SpecPlan, sampled: Sequence[int]) -> StepOutput:
+        """`sampled` holds, row after row, the tokens sampled at every position of the row's chunk
+        (1 + len(draft) each).  Emits 1 + accepted tokens per row, stopping at a finish condition."""
+        B = plan.batch
+        out = StepOutput([], [], [])
+        rows = list(self.rows[:B])
+        now_done: List[Tuple[Request, str]] = []
+        off = 0
+        self.spec_stats["steps"] += 1
+        for i, r in enumerate(rows):
+            d = plan.drafts[i]
+            got = [int(t) for t in sampled[off:off + 1 + len(d)]]
+            off += 1 + len(d)
+            a = verify(d, got)
+            self.spec_stats["drafted"] += len(d)
+            emit = got[:a + 1]
+            reason = None
+            n_emit = 0
+            for tok in emit:
+                r.output_ids.append(tok)
+                n_emit += 1
+                out.req_ids.append(r.req_id); out.token_ids.append(tok); out.finished.append(None)
+                reason = self._finish_reason(r, tok)
+                if reason is not None:
+                    out.finished[-1] = reason
+                    break
+            self.spec_stats["accepted"] += max(0, n_emit - 1)
+            self.last_token[i] = emit[n_emit - 1]
+            self.num_computed[i] += n_emit       # K/V of last_token and of the accepted drafts are in the cache
+            self.remaining[i] -= n_emit
+            if reason is not None:
+                now_done.append((r, reason))
+        for r, reason in now_done[::-1]:          # rows only move down: evict from the highest row first
+            r.finished, r.finish_reason = True, reason
+            self._evict_row(r.row)
+            self._release(r)
+        return out
 
     def _schedule_prefill(self, budget: Optional[int] = None) -> Optional[PrefillPlan]:
         if budget is None:

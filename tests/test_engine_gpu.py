@@ -261,3 +261,60 @@ def test_fp8_w8a8_engine_matches_fp8_oracle(cfg_o):
                 n_checked += 1
             logits = oracle.forward(i, [o[t]])[-1]
     assert n_checked >= 5
+
+
+def test_speculative_decoding_emits_what_plain_decoding_would():
+    """--speculative-config ngram: drafts are verified by one k+1-token forward per sequence through the
+    chunked-prefill path; accepted or not, the emitted tokens must be the target model's own (margin rule
+    against the oracle) -- for greedy AND for seeded temperature sampling (the sampler's noise is a
+    function of (seed, position, token id), so "what plain decoding would sample" is well defined).
+    A proposer that knows the true continuation exercises full and partial acceptance on the device."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    g = torch.Generator().manual_seed(23)
+    prompts = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (37, 90, 150)]
+    prompts[0] = (prompts[0][:8] * 5)[:37]                     # repetitive: the n-gram index finds drafts
+    sp = SamplingParams(max_tokens=24, ignore_eos=True)
+    plain, oracle = _engine(O.TINY, enforce_eager=True)
+    ref = plain.generate(prompts, sp)
+    ref_t = plain.generate(prompts, SamplingParams(max_tokens=24, ignore_eos=True, temperature=0.9, seed=5))
+    del plain
+    spec_cfg = {"method": "ngram", "num_speculative_tokens": 3, "prompt_lookup_max": 4, "prompt_lookup_min": 2}
+    eng, _ = _engine(O.TINY, enforce_eager=True, speculative_config=spec_cfg)
+    assert eng.sched.spec is not None and eng.runner.max_sample == 16 * 4
+    # 1. the real n-gram proposer (acceptance depends on the random model; correctness must not)
+    got = eng.generate(prompts, sp)
+    assert eng.sched.spec_stats["steps"] > 0 and eng.sched.spec_stats["drafted"] > 0
+    _assert_greedy_matches_oracle(oracle, prompts, got)
+    # 2. a proposer that knows the continuation: right for `good` tokens, then wrong
+    truth = {tuple(p): r for p, r in zip(prompts, ref)}
+    n_call = [0]
+
+    def proposer(r, k):
+        n_call[0] += 1
+        t = truth[tuple(r.prompt_ids)]
+        nxt = t[len(r.output_ids):len(r.output_ids) + k]
+        good = n_call[0] % 4
+        return [tok if j < good else (tok + 1) % 500 for j, tok in enumerate(nxt)]
+
+    eng.sched.proposer = proposer
+    before = dict(eng.sched.spec_stats)
+    got2 = eng.generate(prompts, sp)
+    acc = eng.sched.spec_stats["accepted"] - before["accepted"]
+    drafted = eng.sched.spec_stats["drafted"] - before["drafted"]
+    assert 0 < acc < drafted, (acc, drafted)
+    _assert_greedy_matches_oracle(oracle, prompts, got2)
+    agree = sum(a == b for x, y in zip(ref, got2) for a, b in zip(x, y))
+    assert agree >= 0.9 * sum(len(x) for x in ref)            # bf16 k+1-token vs 1-token forwards may flip a near-tie
+    # 3. seeded temperature sampling under speculation: drafts of the sampled continuation are accepted,
+    #    the run is reproducible, and it starts like the plain run (later tokens may part ways after a
+    #    near-tie between a k+1-token and a 1-token forward, as in any batch-shape change)
+    truth = {tuple(p): r for p, r in zip(prompts, ref_t)}
+    spt = SamplingParams(max_tokens=24, ignore_eos=True, temperature=0.9, seed=5)
+    before = dict(eng.sched.spec_stats)
+    got_t = eng.generate(prompts, spt)
+    assert eng.sched.spec_stats["accepted"] > before["accepted"]
+    assert got_t == eng.generate(prompts, spt)
+    assert [x[0] for x in got_t] == [x[0] for x in ref_t]
+    agree = sum(a == b for x, y in zip(ref_t, got_t) for a, b in zip(x, y))
+    assert agree >= 0.5 * sum(len(x) for x in ref_t), (ref_t, got_t)

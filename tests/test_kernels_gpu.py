@@ -495,6 +495,9 @@ def test_paged_attn_decode(ops, Hq, Hkv, D, seq_lens, splits, out_dir):
     (14, 2, 64, [(0, 130), (20, 50)]),
     (4, 1, 128, [(0, 1500)]),
     (16, 2, 128, [(0, 70), (5, 9)]),                      # group of 8 -> 16-token tiles
+    # 528 (tile, kv-head) work items > 2 CTAs x 148 SMs: every CTA of the persistent kernel walks several
+    # tiles with different (odd and even) block counts, so the running barrier phases carry across tiles
+    (32, 8, 128, [(0, 700), (64, 600), (0, 300), (17, 450)]),
 ])
 def test_paged_attn_prefill(ops, Hq, Hkv, D, ctx_q, out_dir):
     g = torch.Generator().manual_seed(len(ctx_q) * 31 + Hq)

@@ -29,12 +29,14 @@ class FakeRunner:
 
     def prefill(self, chunks, starts, tables, sample, decode=None, sample_temps=None, sample_seeds=None):
         call = ("prefill", [list(map(int, c)) for c in chunks], list(map(int, starts)),
-                [list(map(int, t)) for t in tables], [bool(s) for s in sample])
+                [list(map(int, t)) for t in tables], [int(s) for s in sample])
         if decode is not None:     # mixed step: decode rows ride along
             B, last, comp, tab = decode
             call += ((int(B), np.asarray(last[:B]).tolist(), np.asarray(comp[:B]).tolist(), np.asarray(tab[:B]).tolist()),)
         self.calls.append(call)
-        return np.zeros(sum(bool(s) for s in sample), dtype=np.int32)
+        if sample_temps is not None:
+            self.sampler = (np.asarray(sample_temps, dtype=np.float32).tolist(), np.asarray(sample_seeds, dtype=np.uint32).tolist())
+        return np.zeros(sum(int(s) for s in sample), dtype=np.int32)
 
 
 def _worker(rank, port, q):
@@ -54,6 +56,8 @@ def _worker(rank, port, q):
         ("decode", 3, [7, 8, 9], [20, 33, 5], [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]]),
         ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False]),
         ("mixed", [[11, 12, 13]], [32], [[1, 5, 6]], [True], 2, [40, 41], [7, 19], [[2, 0, 0, 0, 0, 0], [3, 4, 0, 0, 0, 0]]),
+        # speculative verification: [last_token, drafts...] per sequence, EVERY row sampled (counts, not flags)
+        ("spec", [[21, 22, 23, 24], [30]], [50, 9], [[1, 2, 3, 4], [5]], [4, 1]),
     ]
     if rank == 0:
         for s in steps:
@@ -66,6 +70,9 @@ def _worker(rank, port, q):
                 tp.bcast_step([E._KIND_DECODE, B], payload)
             elif s[0] == "mixed":
                 eng._bcast_prefill(s[1], s[2], s[3], s[4], (s[5], np.array(s[6]), np.array(s[7]), np.array(s[8])))
+            elif s[0] == "spec":
+                eng._bcast_prefill(s[1], s[2], s[3], s[4], None, np.array([0.0, 0.0, 0.0, 0.0, 0.7], dtype=np.float32),
+                                   np.array([1, 2, 3, 4, 2 ** 32 - 1], dtype=np.uint32))
             else:
                 eng._bcast_prefill(s[1], s[2], s[3], s[4])
         eng.sync_mark(); eng.sync_mark()
@@ -74,7 +81,8 @@ def _worker(rank, port, q):
         q.put(("rank0", dt >= 0.0))
     else:
         E.TPWorker(eng).serve_forever()
-        assert eng.runner.sampler == ([0.0, 0.699999988079071, 1.5], [1, 2 ** 31 + 5, 2 ** 32 - 1])   # bit-exact round trip
+        # sampler inputs of the last step (the speculative one), bit-exact round trip
+        assert eng.runner.sampler == ([0.0, 0.0, 0.0, 0.0, 0.699999988079071], [1, 2, 3, 4, 2 ** 32 - 1])
         q.put(("rank1", eng.runner.calls))
     dist.destroy_process_group()
 
@@ -94,9 +102,10 @@ def test_step_broadcast_roundtrip():
     calls = got["rank1"]
     assert calls[0] == ("decode", 3, [7, 8, 9], [20, 33, 5],
                         [[1, 2, 0, 0, 0, 0], [3, 4, 5, 0, 0, 0], [6, 0, 0, 0, 0, 0]])
-    assert calls[1] == ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [True, False])
-    assert calls[2] == ("prefill", [[11, 12, 13]], [32], [[1, 5, 6]], [True],
+    assert calls[1] == ("prefill", [[5, 6, 7, 8], [9, 10]], [0, 16], [[2, 3], [4]], [1, 0])
+    assert calls[2] == ("prefill", [[11, 12, 13]], [32], [[1, 5, 6]], [1],
                         (2, [40, 41], [7, 19], [[2, 0, 0, 0, 0, 0], [3, 4, 0, 0, 0, 0]]))
+    assert calls[3] == ("prefill", [[21, 22, 23, 24], [30]], [50, 9], [[1, 2, 3, 4], [5]], [4, 1])
 
 
 def _stress(rank, port, q, channel):

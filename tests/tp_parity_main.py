@@ -61,6 +61,18 @@ def main():
         res["checks"].append({"seq": i, "checked": n_chk, "agree": n_ok})
         if n_ok != n_chk or n_chk < (3 if family == "dense" else 1):
             res["ok"] = False
+    # sampled requests across vocab shards: the in-kernel Gumbel-max draw is keyed by (seed, position,
+    # GLOBAL vocab index), so a seed reproduces its tokens, another seed does not, and nucleus rows
+    # (top_p < 1) go through the all-rank logits gather; top_p -> 0 must collapse onto greedy
+    sp = dict(max_tokens=12, ignore_eos=True)
+    a = eng.generate(prompts[:2], SamplingParams(temperature=1.3, seed=11, **sp))
+    b = eng.generate(prompts[:2], SamplingParams(temperature=1.3, seed=11, **sp))
+    d = eng.generate(prompts[:2], SamplingParams(temperature=1.3, seed=12, **sp))
+    n = eng.generate(prompts[:2], SamplingParams(temperature=1.0, top_p=1e-6, seed=3, **sp))
+    res["sampled"] = {"reproducible": a == b, "seed_matters": a != d, "differs_from_greedy": a != [o[:12] for o in outs[:2]],
+                      "nucleus_top_p_0_is_greedy": n == [o[:12] for o in outs[:2]]}
+    if not all(res["sampled"].values()):
+        res["ok"] = False
     eng.shutdown()
     print("TP_PARITY " + json.dumps(res), flush=True)
     if not res["ok"]:
