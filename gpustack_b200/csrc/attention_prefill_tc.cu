@@ -89,7 +89,8 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* o_full = bars + 13;
   uint64_t* q_empty = bars + 14;    // the tile's last Q K^T has retired: the Q buffer may be reloaded
   uint64_t* o_empty = bars + 15;    // the epilogue has read O out of tensor memory (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* p_full_b = bars + 16;   // p_full of the odd S buffer (p_full itself: the even one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,7 +107,8 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);     // one arrive per softmax warp
+    mbar_init(p_full, 4);     // one arrive per softmax warp; ONE BARRIER PER S BUFFER (see the softmax loop)
+    mbar_init(p_full_b, 4);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(q_empty, 1);
@@ -248,7 +250,7 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
             issue_s(gb + 1);
             if (j + 2 == n_blocks) umma_commit(q_empty);   // the tile's last Q K^T: Q may be reloaded
           }
-          mbar_wait_guarded(p_full, gb & 1);
+          mbar_wait_guarded((gb & 1) ? p_full_b : p_full, (gb >> 1) & 1);
           tc_fence_after();
           if (j == 0 && it > 0) {           // PV_0 overwrites O: the previous tile's epilogue must have read it
             mbar_wait_guarded(o_empty, (it - 1) & 1);
@@ -374,9 +376,16 @@ paged_attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]));
           fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
         }
+        // p_full is one barrier PER S BUFFER.  With a single count-4 barrier a fast warp could finish
+        // block gb + 1 (its S is issued one block ahead and is already waiting) and arrive a second time
+        // while a slow warp is still inside block gb: the phase would complete early, PV would read P rows
+        // that are not written yet and the next Q K^T would overwrite S rows still being read (seen on
+        // hardware as NaN rows once the persistent loop let the warps drift apart).  With one barrier per
+        // buffer the second arrival lands on the other barrier, and block gb + 2 (same barrier again)
+        // cannot start before the MMA warp has consumed phase gb.
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive((gb & 1) ? p_full_b : p_full);
       }
 
       // ---- epilogue: O / l -> bf16 -> out[token, head, :]

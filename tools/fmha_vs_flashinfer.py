@@ -88,7 +88,9 @@ def main():
         att = att.masked_fill(torch.triu(torch.ones(seqlen, seqlen, dtype=torch.bool, device=dev), 1), float("-inf"))
         ref = torch.softmax(att, -1) @ vv
         ref_err = (out[sq * seqlen:(sq + 1) * seqlen, :D].float() - ref).abs().max().item()
+        bad = torch.isnan(out.float()).reshape(T, HQ, D).any(-1).nonzero()[:12].tolist()      # (token, head) pairs
         line = {"shape": f"{batch} x {seqlen} causal, Hq {HQ} / Hkv {HKV} x {D}, page {PAGE}", "flops": flops,
+                "nan_rows_ours_after_timing": bad, "page0_owner": (bt == 0).nonzero()[:2].tolist(),
                 "ours_us": round(us, 2), "ours_tflops": round(flops / us / 1e6, 1),
                 "ours_max_abs_err_vs_fp32_reference": ref_err}
         if fi_ctx is None:
