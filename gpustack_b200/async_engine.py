@@ -287,64 +287,31 @@ class EngineClient(_StreamHub):
     """Runs in the FRONTEND process: same interface as AsyncEngine, transport = a pipe to an
     EngineCoreServer."""
 
-    def __init__(self, conn, reader_thread: bool = True):
-        """reader_thread=False: the owner calls attach_loop() from its running event loop and the pipe is
-        read ON the loop (loop.add_reader).  A reader thread has to take the GIL from a busy event loop for
-        every engine step -- up to one switch interval (5 ms) of added inter-token latency per step at a
-        few hundred concurrent streams."""
+    def __init__(self, conn):
         super().__init__()
         self.conn = conn
         self._send_lock = threading.Lock()
         self._snap = {"running": 0, "waiting": 0, "kv_usage": 0.0, "preemptions": 0, "generation_tokens": 0,
                       "prefix_queries": 0, "prefix_hits": 0}
         self._last_msg = time.monotonic()
-        self._loop: Optional[asyncio.AbstractEventLoop] = None
-        self._thread = None
-        if reader_thread:
-            self._thread = threading.Thread(target=self._reader, name="b200-engine-client", daemon=True)
-            self._thread.start()
-
-    def attach_loop(self, loop: asyncio.AbstractEventLoop) -> None:
-        self._loop = loop
-        loop.add_reader(self.conn.fileno(), self._on_readable)
-
-    def _handle(self, msg) -> None:
-        self._last_msg = time.monotonic()
-        kind = msg[0]
-        if kind == "out":
-            self._snap = msg[4]
-            if self._loop is not None:          # already on the loop: no cross-thread hop
-                now = self._last_msg
-                get = self._streams.get
-                for rid, tok, fin in zip(msg[1], msg[2], msg[3]):
-                    ent = get(rid)
-                    if ent is not None:
-                        ent[1].put_nowait(([tok], fin, now))
-            else:
-                self._dispatch(msg[1], msg[2], msg[3])
-        elif kind == "beat":
-            self._snap = msg[1]
-        elif kind == "invalid":
-            self._fail_request(msg[1], ValueError(msg[2]))
-        elif kind == "died":
-            raise RuntimeError(msg[1])
-
-    def _on_readable(self) -> None:
-        try:
-            while self.conn.poll(0):
-                self._handle(self.conn.recv())
-        except BaseException as e:  # noqa: BLE001  (EOF: the engine core went away)
-            self.errored = e
-            try:
-                self._loop.remove_reader(self.conn.fileno())
-            except Exception:  # noqa: BLE001
-                pass
-            self._fail_all()
+        self._thread = threading.Thread(target=self._reader, name="b200-engine-client", daemon=True)
+        self._thread.start()
 
     def _reader(self) -> None:
         try:
             while True:
-                self._handle(self.conn.recv())
+                msg = self.conn.recv()
+                self._last_msg = time.monotonic()
+                kind = msg[0]
+                if kind == "out":
+                    self._snap = msg[4]
+                    self._dispatch(msg[1], msg[2], msg[3])
+                elif kind == "beat":
+                    self._snap = msg[1]
+                elif kind == "invalid":
+                    self._fail_request(msg[1], ValueError(msg[2]))
+                elif kind == "died":
+                    raise RuntimeError(msg[1])
         except BaseException as e:  # noqa: BLE001
             self.errored = e
             self._fail_all()
@@ -366,8 +333,7 @@ class EngineClient(_StreamHub):
         return dict(self._snap)
 
     def is_healthy(self) -> bool:
-        alive = self._thread.is_alive() if self._thread is not None else self._loop is not None
-        return self.errored is None and alive and time.monotonic() - self._last_msg < 30.0
+        return self.errored is None and self._thread.is_alive() and time.monotonic() - self._last_msg < 30.0
 
     def shutdown(self) -> None:
         try:

@@ -17,24 +17,8 @@ def run_frontend(conn, host: str, port: int, served_model_name: str, max_model_l
 
     logging.basicConfig(level=getattr(logging, log_level.upper(), logging.WARNING))
     tok = load_tokenizer(model_path, vocab_size, bos, eos)
-    client = EngineClient(conn, reader_thread=False)
+    client = EngineClient(conn)
     app = create_app(client, tok, served_model_name, max_model_len)
-
-    @app.on_event("startup")
-    async def _attach():          # the pipe from the engine core is read on the serving loop itself
-        import asyncio
-
-        client.attach_loop(asyncio.get_running_loop())
-
-    import os
-    prof = None
-    if os.environ.get("B200_FRONTEND_PROFILE"):
-        import cProfile, signal
-        prof = cProfile.Profile()
-        def _dump(*_):
-            prof.disable(); prof.dump_stats(os.environ["B200_FRONTEND_PROFILE"]); os._exit(0)
-        signal.signal(signal.SIGTERM, _dump)
-        prof.enable()
     try:
         uvicorn.run(app, host=host, port=port, log_level=log_level, access_log=False, timeout_keep_alive=5,
                     backlog=4096)

@@ -79,6 +79,7 @@ def main():
     ap.add_argument("-n", "--num-requests", type=int, default=1024)
     ap.add_argument("--output-len", type=int, default=128)
     ap.add_argument("--harness", action="store_true", help="drive with the reference's benchmark_serving.py instead")
+    ap.add_argument("--clients", type=int, default=1, help="split the load over this many client PROCESSES")
     a = ap.parse_args()
     from gpustack_b200.frontend import spawn_frontend
 
@@ -105,8 +106,22 @@ def main():
     else:
         cmd = [sys.executable, "-m", "gpustack_b200.bench_client", "--url", f"http://127.0.0.1:{port}", "-m", "stub",
                "-n", str(a.num_requests), "-c", str(a.concurrency), "--input-len", "512", "--output-len", str(a.output_len)]
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
-    line = r.stdout[r.stdout.index("{"):] if "{" in r.stdout else r.stdout + r.stderr[-500:]
+    if a.clients > 1 and not a.harness:
+        k = a.clients
+        cmd[cmd.index("-n") + 1] = str(a.num_requests // k)
+        cmd[cmd.index("-c") + 1] = str(a.concurrency // k)
+        t0 = time.time()
+        ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for _ in range(k)]
+        outs = [p.communicate(timeout=900)[0] for p in ps]
+        rs = [json.loads(o[o.index("{"):]) for o in outs]
+        wall = max(x["total_time_s"] for x in rs)
+        line = json.dumps({"clients": k, "successful": sum(x["successful"] for x in rs),
+                           "output_tok_s": sum(x["completion_tokens"] for x in rs) / wall, "total_time_s": wall,
+                           "tpot_ms_p50": float(np.median([x["tpot_ms_p50"] for x in rs])),
+                           "ttft_ms_p50": float(np.median([x["ttft_ms_p50"] for x in rs]))})
+    else:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        line = r.stdout[r.stdout.index("{"):] if "{" in r.stdout else r.stdout + r.stderr[-500:]
     waves = -(-a.num_requests // a.concurrency)
     ideal_s = waves * (a.prefill_ms / 1e3 * a.concurrency * 512 / 8192 + (a.output_len - 1) * a.step_ms / 1e3)
     print(json.dumps({"ideal_output_tok_s_of_the_stub": round(a.num_requests * a.output_len / ideal_s, 1),
