@@ -50,6 +50,13 @@ def build_parser() -> argparse.ArgumentParser:
                    help='JSON as the GPUStack launcher composes it (gpustack/worker/backends/vllm.py:333-367), e.g. '
                         '\'{"method": "ngram", "num_speculative_tokens": 3, "prompt_lookup_max": 4, '
                         '"prompt_lookup_min": 2}\'; draft-model methods (eagle3, mtp) run without speculation')
+    s.add_argument("--kv-transfer-config", default=None,
+                   help='what GPUStack\'s launcher passes when the model has extended_kv_cache enabled '
+                        '(\'{"kv_connector":"LMCacheConnectorV1","kv_role":"kv_both"}\', worker/backends/vllm.py:468-483): '
+                        'turns on the host-memory tier of the prefix cache, sized by LMCACHE_MAX_LOCAL_CPU_SIZE (GiB, '
+                        'the env the launcher sets; default 5)')
+    s.add_argument("--kv-host-cache-gib", type=float, default=None,
+                   help="host-memory tier of the prefix cache in GiB (native spelling of the above)")
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
     est = sub.add_parser("estimate", help="print the engine's exact VRAM requirement (GPUSTACK_MODEL_VRAM_CLAIM)")
@@ -81,7 +88,18 @@ def _engine_config(args, tp: int):
         log.warning("speculative method %r needs a draft model and is not implemented: serving WITHOUT speculation "
                     "(results are unaffected, only latency)", spec.method)
         spec = None
-    return EngineConfig(speculative_config=spec.to_dict() if spec is not None else None, model=args.model, served_model_name=(args.served_model_name or [None])[0],
+    host_gib = args.kv_host_cache_gib
+    if host_gib is None and args.kv_transfer_config:
+        import json
+
+        kt = json.loads(args.kv_transfer_config)
+        if "LMCache" in str(kt.get("kv_connector", "")):
+            # LMCACHE_CHUNK_SIZE is accepted and unused: this tier works at KV-block (16-token) granularity
+            host_gib = float(os.environ.get("LMCACHE_MAX_LOCAL_CPU_SIZE", "5"))
+        else:
+            log.warning("kv connector %r is not implemented; serving without an extended KV cache", kt.get("kv_connector"))
+    return EngineConfig(speculative_config=spec.to_dict() if spec is not None else None,
+                        kv_host_cache_gib=float(host_gib or 0.0), model=args.model, served_model_name=(args.served_model_name or [None])[0],
                         max_model_len=args.max_model_len, tensor_parallel_size=tp,
                         gpu_memory_utilization=args.gpu_memory_utilization, max_num_seqs=args.max_num_seqs,
                         max_num_batched_tokens=args.max_num_batched_tokens,

@@ -256,6 +256,7 @@ class EngineConfig:
     enable_prefix_caching: bool = True        # reuse full KV blocks across requests (reference engine default)
     quantization: Optional[str] = None        # None | "fp8" (W8A8: online per-tensor weights, per-token activations)
     mixed_steps: bool = True                  # prefill steps also carry the running sequences' decode tokens
+    kv_host_cache_gib: float = 0.0            # extended KV cache: pinned host memory for evicted prefix blocks (0 = off)
     # --speculative-config as a dict ({"method": "ngram", "num_speculative_tokens": k, ...}), None = off
     speculative_config: Optional[dict] = None
     seed: int = 0

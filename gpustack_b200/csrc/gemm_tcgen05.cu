@@ -387,6 +387,10 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   using Cfg = Gemm2Cfg<BLOCK_X>;
   constexpr int kElemsK = FP8 ? 2 * kBlockK : kBlockK;   // elements per 128-byte k-block
   constexpr int STAGES = Cfg::kStages;
+  // bits 16.. of group_m: L2 eviction-priority overrides for the two operand streams (A/B runs,
+  // B200_GEMM_HINTS; 0 = the built-in choice)
+  const int hint_code = group_m >> 16;
+  group_m &= 0xffff;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -441,7 +445,13 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
-      const uint64_t hint_w = (m_tiles > 1) ? kEvictNormal : kEvictFirst;
+      uint64_t hint_w = (m_tiles > 1) ? kEvictNormal : kEvictFirst;
+      uint64_t hint_x = kEvictLast;
+      {
+        const uint64_t tab[4] = {0, kEvictFirst, kEvictNormal, kEvictLast};
+        if (hint_code & 3) hint_w = tab[hint_code & 3];
+        if ((hint_code >> 2) & 3) hint_x = tab[(hint_code >> 2) & 3];
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int u = first_unit; u < total_units; u += unit_stride) {
@@ -458,7 +468,7 @@ __device__ __forceinline__ void gemm_2sm_body(const CUtensorMap& tmap_w, const C
           mbar_expect_tx_cluster(mapa_u32(&full_bar[stage], 0), Cfg::kStageBytes);
           tma_load_2d_2sm(a, &tmap_w, &full_bar[stage], k0 + kb * kElemsK, w_row, hint_w);
           tma_load_2d_2sm(b, &tmap_x, &full_bar[stage], k0 + kb * kElemsK,
-                          c.m_tile * BLOCK_X + (int)crank * Cfg::kHalf, kEvictLast);
+                          c.m_tile * BLOCK_X + (int)crank * Cfg::kHalf, hint_x);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -663,7 +673,15 @@ static int gemm_group_m(int m_tiles, int K) {
     const long long tile_bytes = 256LL * (long long)K * 2;   // one m-tile of activations (bf16 element count)
     while (g > 4 && (long long)g * tile_bytes > (64LL << 20)) g >>= 1;
   }
-  return m_tiles < g ? m_tiles : g;
+  static int hints = -1;
+  if (hints < 0) {
+    // "w,x" with 1 = evict-first, 2 = normal, 3 = evict-last, 0 = built-in (weights normal, activations last)
+    const char* e = getenv("B200_GEMM_HINTS");
+    hints = 0;
+    if (e && e[0] >= '0' && e[0] <= '3' && e[1] == ',' && e[2] >= '0' && e[2] <= '3')
+      hints = (e[0] - '0') | ((e[2] - '0') << 2);
+  }
+  return (m_tiles < g ? m_tiles : g) | (hints << 16);
 }
 
 static bool gemm_2sm_enabled() {

@@ -27,6 +27,7 @@ from .weights import (ModelWeights, lazy_random_source, load_safetensors_dir, ra
 log = logging.getLogger("b200.engine")
 
 _KIND_STOP, _KIND_DECODE, _KIND_PREFILL, _KIND_SYNC, _KIND_MAXELAPSED, _KIND_GATHER, _KIND_MIXED = 0, 1, 2, 3, 4, 5, 6
+_KIND_SWAP = 7          # extended KV cache: ordered device<->host block copies, executed before the step that follows
 
 
 class ShmStepChannel:
@@ -201,10 +202,15 @@ class LLMEngine:
         self.num_blocks = n
         self.runner.init_kv_cache(n)
         self.runner.capture_graphs()
+        # extended KV cache: evicted prefix blocks go to pinned host memory (same slot count on every rank)
+        host_slots = 0
+        if ecfg.kv_host_cache_gib > 0 and ecfg.enable_prefix_caching:
+            host_slots = int(ecfg.kv_host_cache_gib * (1 << 30)) // self.runner.kv_block_bytes()
+        self.runner.init_host_kv(host_slots)
         self.sched = Scheduler(n, ecfg.block_size, ecfg.max_num_seqs, ecfg.max_num_batched_tokens,
                                ecfg.max_model_len, mcfg.eos_token_ids or mcfg.eos_token_id, ecfg.enable_prefix_caching,
                                mixed_steps=ecfg.mixed_steps, speculative=ecfg.speculative(),
-                               max_sample_rows=self.runner.max_sample)
+                               max_sample_rows=self.runner.max_sample, kv_host_slots=host_slots)
         self.requests: Dict[str, Request] = {}
         self.counters = {"prompt_tokens": 0, "generation_tokens": 0, "finished": 0, "steps": 0}
         self.step_time = {"prefill": 0.0, "decode": 0.0}
@@ -268,6 +274,11 @@ class LLMEngine:
     # ------------------------------------------------------------------ one iteration
     def step(self) -> Optional[StepOutput]:
         plan = self.sched.schedule()
+        swaps = self.sched.pool.take_swap_ops() if self.sched.pool.host_slots else None
+        if swaps:       # host-tier copies decided while scheduling: on the stream BEFORE this step's kernels
+            if self.tp:
+                self.tp.bcast_step([_KIND_SWAP, len(swaps)], np.asarray(swaps, dtype=np.int32).reshape(-1))
+            self.runner.kv_swap(swaps)
         if plan is None:
             return None
         t0 = time.perf_counter()
@@ -448,6 +459,9 @@ class TPWorker:
                 continue
             if kind == _KIND_GATHER:
                 run.gather_logits_rows(p[:h[1]].tolist())     # rank 0 samples; this rank only contributes
+                continue
+            if kind == _KIND_SWAP:
+                run.kv_swap(p[:3 * h[1]].reshape(-1, 3).tolist())
                 continue
             if kind == _KIND_DECODE:
                 B = h[1]

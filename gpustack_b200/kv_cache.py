@@ -12,6 +12,14 @@ is keyed by a chained digest of (parent digest, its 16 token ids).  A finished o
 sequence leaves its blocks in the free queue *with* their keys, so a later request whose prompt
 starts with the same tokens re-attaches them (ref-count + 1) and starts its prefill behind them.
 The free queue is LRU: a block loses its key only when it is handed out again.
+
+Extended KV cache (GPUStack's `extended_kv_cache`, which its vLLM launcher turns into
+`--kv-transfer-config {"kv_connector":"LMCacheConnectorV1",...}` + `LMCACHE_MAX_LOCAL_CPU_SIZE`,
+gpustack/worker/backends/vllm.py:256-275,468-483): an optional SECOND TIER in pinned host memory.  A keyed
+block that is evicted from the device pool is copied to a host slot first; a later prompt whose chain of
+digests continues into the host tier gets those blocks copied back instead of recomputed.  This module
+only does the bookkeeping and records the copies as an ordered list of swap operations; the engine executes
+them on the step's stream before the step's kernels (runner.kv_swap).
 """
 from __future__ import annotations
 
@@ -44,12 +52,21 @@ def block_digests(token_ids: Sequence[int], block_size: int, have: Optional[List
 
 
 class BlockPool:
-    def __init__(self, num_blocks: int, block_size: int = 16, enable_prefix_caching: bool = False):
+    def __init__(self, num_blocks: int, block_size: int = 16, enable_prefix_caching: bool = False,
+                 host_slots: int = 0):
         if num_blocks < 2:
             raise ValueError("need at least 2 KV blocks")
         self.num_blocks = num_blocks
         self.block_size = block_size
         self.caching = enable_prefix_caching
+        # host tier: digest -> slot (LRU, oldest first), free slots, ordered swap operations of this step
+        self.host_slots = host_slots if enable_prefix_caching else 0
+        self._host: "OrderedDict[bytes, int]" = OrderedDict()
+        self._host_free: List[int] = list(range(self.host_slots - 1, -1, -1))
+        self._host_pinned: Dict[bytes, int] = {}
+        self.swap_ops: List[tuple] = []          # (SWAP_OUT | SWAP_IN, device block, host slot), in execution order
+        self.host_hits = 0                       # tokens served from the host tier
+        self.host_stored = 0                     # blocks ever copied out
         # free queue, head = next block handed out; block 0 = null block, never in the queue
         self._free: "OrderedDict[int, None]" = OrderedDict((b, None) for b in range(1, num_blocks))
         self._ref = [0] * num_blocks
@@ -86,9 +103,62 @@ class BlockPool:
             if k is not None:                      # evicted from the prefix cache
                 del self._cached[k]
                 self._key[b] = None
+                if self.host_slots:
+                    self._offload(b, k)
             self._ref[b] = 1
             out.append(b)
         return out
+
+    # ------------------------------------------------------------------ host tier
+    SWAP_OUT, SWAP_IN = 0, 1
+
+    def _offload(self, block: int, key: bytes) -> None:
+        """The device copy of `key` is about to be overwritten: keep it in a host slot."""
+        if key in self._host:
+            self._host.move_to_end(key)          # an older host copy is still valid
+            return
+        if key in self._host_pinned:
+            return
+        if self._host_free:
+            slot = self._host_free.pop()
+        elif self._host:
+            _, slot = self._host.popitem(last=False)     # host LRU victim
+        else:
+            return                               # every slot is pinned by loads of this step: drop the block
+        self._host[key] = slot
+        self.swap_ops.append((self.SWAP_OUT, block, slot))
+        self.host_stored += 1
+
+    def match_tiers(self, digests: Sequence[bytes]) -> List[tuple]:
+        """Longest run of cached blocks over BOTH tiers: [(True, device block) | (False, digest)] (no state change)."""
+        out: List[tuple] = []
+        if not self.caching:
+            return out
+        for d in digests:
+            b = self._cached.get(d)
+            if b is not None:
+                out.append((True, b))
+            elif d in self._host:
+                out.append((False, d))
+            else:
+                break
+        return out
+
+    def pin_host(self, digests: Sequence[bytes]) -> None:
+        """Host entries about to be loaded must survive the evictions of the allocation that follows."""
+        for d in digests:
+            self._host_pinned[d] = self._host.pop(d)
+
+    def load_from_host(self, digest: bytes, block: int) -> None:
+        """Queue the copy host slot -> device `block` and put the (pinned) entry back as most recently used."""
+        slot = self._host_pinned.pop(digest)
+        self._host[digest] = slot
+        self.swap_ops.append((self.SWAP_IN, block, slot))
+        self.host_hits += self.block_size
+
+    def take_swap_ops(self) -> List[tuple]:
+        ops, self.swap_ops = self.swap_ops, []
+        return ops
 
     def free(self, blocks: List[int]) -> None:
         if self.caching:
@@ -143,6 +213,8 @@ class BlockPool:
         for d, b in self._cached.items():
             self._key[b] = None
         self._cached.clear()
+        self._host_free.extend(self._host.values())
+        self._host.clear()
 
 
 class SequenceBlocks:

@@ -180,6 +180,51 @@ class ModelRunner:
         self.k_cache = [torch.zeros(shape, dtype=BF16, device=self.device) for _ in range(self.mcfg.num_hidden_layers)]
         self.v_cache = [torch.zeros(shape, dtype=BF16, device=self.device) for _ in range(self.mcfg.num_hidden_layers)]
 
+    # ------------------------------------------------------------------------------ extended KV cache (host tier)
+    def init_host_kv(self, slots: int) -> None:
+        """Pinned host memory for `slots` KV blocks (all layers, K and V of this rank's kv-heads) plus a
+        device staging area; see kv_cache.BlockPool (host tier) for who decides what moves."""
+        self.host_slots = int(slots)
+        if self.host_slots <= 0:
+            return
+        L = self.mcfg.num_hidden_layers
+        shape = (L, 2, self.Hkv, self.block_size, self.D)
+        self._swap_batch = 32
+        self.host_kv = torch.empty((self.host_slots,) + shape, dtype=BF16, pin_memory=True)
+        self.swap_stage = torch.empty((self._swap_batch,) + shape, dtype=BF16, device=self.device)
+
+    def kv_swap(self, ops_: Sequence[Sequence[int]]) -> None:
+        """Execute the pool's swap operations IN ORDER on the current stream (before the step's kernels):
+        (0, block, slot) copies a device block to a host slot, (1, block, slot) the other way.  Runs of
+        the same kind are batched: one gather / scatter per layer through the staging area, one pinned
+        transfer per block."""
+        i, n_ops = 0, len(ops_)
+        L = self.mcfg.num_hidden_layers
+        while i < n_ops:
+            kind = int(ops_[i][0])
+            j = i
+            while j < n_ops and int(ops_[j][0]) == kind and j - i < self._swap_batch:
+                j += 1
+            blocks = torch.tensor([int(o[1]) for o in ops_[i:j]], dtype=torch.long, device=self.device)
+            slots = [int(o[2]) for o in ops_[i:j]]
+            n = j - i
+            st = self.swap_stage[:n]
+            if kind == 0:
+                for l in range(L):
+                    torch.index_select(self.k_cache[l], 0, blocks, out=st[:, l, 0])
+                    torch.index_select(self.v_cache[l], 0, blocks, out=st[:, l, 1])
+                for q, slot in enumerate(slots):
+                    self.host_kv[slot].copy_(st[q], non_blocking=True)
+                self.stats["kv_swap_out_blocks"] = self.stats.get("kv_swap_out_blocks", 0) + n
+            else:
+                for q, slot in enumerate(slots):
+                    st[q].copy_(self.host_kv[slot], non_blocking=True)
+                for l in range(L):
+                    self.k_cache[l].index_copy_(0, blocks, st[:, l, 0])
+                    self.v_cache[l].index_copy_(0, blocks, st[:, l, 1])
+                self.stats["kv_swap_in_blocks"] = self.stats.get("kv_swap_in_blocks", 0) + n
+            i = j
+
     # ------------------------------------------------------------------------------ layers
     def _quant(self, x: torch.Tensor, T: int):
         """bf16 activations -> (e4m3 [T,K], per-token scales [T]) in the shared fp8 staging buffer."""

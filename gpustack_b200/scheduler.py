@@ -126,11 +126,12 @@ class StepOutput:
 class Scheduler:
     def __init__(self, num_blocks: int, block_size: int, max_num_seqs: int, max_num_batched_tokens: int,
                  max_model_len: int, eos_token_id, enable_prefix_caching: bool = False, mixed_steps: bool = True,
-                 speculative: Optional[SpeculativeConfig] = None, max_sample_rows: Optional[int] = None):
+                 speculative: Optional[SpeculativeConfig] = None, max_sample_rows: Optional[int] = None,
+                 kv_host_slots: int = 0):
         """eos_token_id: one id, an iterable of ids (every turn terminator of the checkpoint), or None.
         speculative: n-gram speculative decoding on pure decode steps (spec_decode.py); max_sample_rows
         bounds the rows one step may sample (the runner's logits buffer)."""
-        self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching)
+        self.pool = BlockPool(num_blocks, block_size, enable_prefix_caching, host_slots=kv_host_slots)
         self.block_size = block_size
         self.max_num_seqs = max_num_seqs
         self.max_tokens_per_step = max_num_batched_tokens
@@ -355,19 +356,30 @@ class Scheduler:
             if len(self.rows) + len(self.prefilling) >= self.max_num_seqs:
                 break
             target = r.prefill_target
-            hit: List[int] = []
+            entries: List[tuple] = []        # cached prefix, block by block: (True, device block) | (False, digest in the host tier)
             if self.pool.caching:
                 # the last token is always recomputed: its logits are what gets sampled
                 block_digests(r.all_ids, self.block_size, r.digests, upto_blocks=(target - 1) // self.block_size)
-                hit = self.pool.match_prefix(r.digests[: (target - 1) // self.block_size])
-            need = self._blocks_for(target + 1) - len(hit)
+                entries = self.pool.match_tiers(r.digests[: (target - 1) // self.block_size])
+            hit = [b for on_dev, b in entries if on_dev]
+            need = self._blocks_for(target + 1) - len(hit)      # host-tier hits need a device block each
             # keep one spare block per running sequence so that decode does not preempt at once
             if need + self.pool.count_free(hit) + len(self.rows) > self.pool.num_free:
                 break
             self.waiting.popleft()
             self.pool.attach(hit)
-            r.blocks = hit + self.pool.allocate(need)
-            r.num_computed = len(hit) * self.block_size
+            self.pool.pin_host([d for on_dev, d in entries if not on_dev])
+            fresh = iter(self.pool.allocate(need))
+            r.blocks = []
+            for on_dev, x in entries:
+                if on_dev:
+                    r.blocks.append(x)
+                else:                          # copied back from host memory before this step's kernels run
+                    b = next(fresh)
+                    self.pool.load_from_host(x, b)
+                    r.blocks.append(b)
+            r.blocks.extend(fresh)
+            r.num_computed = len(entries) * self.block_size
             if self.pool.caching:
                 self.pool.queries += target
                 self.pool.hits += r.num_computed

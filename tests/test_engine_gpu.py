@@ -321,3 +321,47 @@ def test_speculative_decoding_emits_what_plain_decoding_would():
     assert [x[0] for x in got_t] == [x[0] for x in ref_t]
     agree = sum(a == b for x, y in zip(ref_t, got_t) for a, b in zip(x, y))
     assert agree >= 0.5 * sum(len(x) for x in ref_t), (ref_t, got_t)
+
+
+def test_extended_kv_cache_brings_evicted_prefixes_back_from_host_memory():
+    """Host-memory tier of the prefix cache (GPUStack `extended_kv_cache` -> `--kv-transfer-config` LMCache):
+    blocks evicted from a small device pool are copied to pinned host memory and copied back -- bit for bit --
+    when a prompt with that prefix returns; the prompt is then not recomputed and the output still obeys the
+    oracle margin rule."""
+    from gpustack_b200.scheduler import SamplingParams
+
+    g = torch.Generator().manual_seed(31)
+    A = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (120, 97, 140)]
+    B = [torch.randint(3, 500, (n,), generator=g).tolist() for n in (150, 150, 150, 150)]
+    sp = SamplingParams(max_tokens=6, ignore_eos=True)
+    eng, oracle = _engine(O.TINY, enforce_eager=True, blocks=44, max_num_seqs=4, enable_prefix_caching=True,
+                          kv_host_cache_gib=1.0 / 64)
+    run = eng.runner
+    assert run.host_slots > 40 and eng.sched.pool.host_slots == run.host_slots
+    # 1. the copy primitives: out, clobber, in == identity on every layer
+    blocks, slots = [3, 5, 7, 11], [0, 1, 2, 3]
+    for l in range(len(run.k_cache)):
+        run.k_cache[l].normal_(); run.v_cache[l].normal_()
+    keep = [(run.k_cache[l][blocks].clone(), run.v_cache[l][blocks].clone()) for l in range(len(run.k_cache))]
+    run.kv_swap([(0, b, s) for b, s in zip(blocks, slots)])
+    for l in range(len(run.k_cache)):
+        run.k_cache[l][blocks] = 0; run.v_cache[l][blocks] = 0
+    run.kv_swap([(1, b, s) for b, s in zip(blocks[::-1], slots[::-1])])
+    torch.cuda.synchronize()
+    for l, (k, v) in enumerate(keep):
+        assert torch.equal(run.k_cache[l][blocks], k) and torch.equal(run.v_cache[l][blocks], v), l
+    for l in range(len(run.k_cache)):
+        run.k_cache[l].zero_(); run.v_cache[l].zero_()
+    # 2. A fills the cache, B pushes A's blocks out to the host tier, A comes back
+    first = eng.generate(A, sp)
+    computed_first = run.stats["prefill_tokens"]
+    eng.generate(B, sp)
+    assert eng.sched.pool.host_stored > 0 and run.stats.get("kv_swap_out_blocks", 0) == eng.sched.pool.host_stored
+    before = run.stats["prefill_tokens"]
+    again = eng.generate(A, sp)
+    recomputed = run.stats["prefill_tokens"] - before
+    assert run.stats.get("kv_swap_in_blocks", 0) > 0 and eng.sched.pool.host_hits > 0
+    assert recomputed < 0.4 * computed_first, (recomputed, computed_first)      # most of A came from host memory
+    _assert_greedy_matches_oracle(oracle, A, first)
+    _assert_greedy_matches_oracle(oracle, A, again)
+    assert [x[0] for x in again] == [x[0] for x in first]
