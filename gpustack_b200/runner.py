@@ -211,8 +211,8 @@ class ModelRunner:
             st = self.swap_stage[:n]
             if kind == 0:
                 for l in range(L):
-                    torch.index_select(self.k_cache[l], 0, blocks, out=st[:, l, 0])
-                    torch.index_select(self.v_cache[l], 0, blocks, out=st[:, l, 1])
+                    st[:, l, 0].copy_(self.k_cache[l].index_select(0, blocks))
+                    st[:, l, 1].copy_(self.v_cache[l].index_select(0, blocks))
                 for q, slot in enumerate(slots):
                     self.host_kv[slot].copy_(st[q], non_blocking=True)
                 self.stats["kv_swap_out_blocks"] = self.stats.get("kv_swap_out_blocks", 0) + n

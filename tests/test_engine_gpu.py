@@ -352,6 +352,7 @@ def test_extended_kv_cache_brings_evicted_prefixes_back_from_host_memory():
         assert torch.equal(run.k_cache[l][blocks], k) and torch.equal(run.v_cache[l][blocks], v), l
     for l in range(len(run.k_cache)):
         run.k_cache[l].zero_(); run.v_cache[l].zero_()
+    run.stats["kv_swap_out_blocks"] = run.stats["kv_swap_in_blocks"] = 0
     # 2. A fills the cache, B pushes A's blocks out to the host tier, A comes back
     first = eng.generate(A, sp)
     computed_first = run.stats["prefill_tokens"]
