@@ -606,7 +606,7 @@ def run_ours(a):
     gd = timer.get("gemm_decode", {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
     ach = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] else 0.0
     traffic, traffic_src = None, None
-    tp_ = ROOT / "profiles" / "r1_gemm_prefill_traffic.json"
+    tp_ = ROOT / "profiles" / "r2_gemm_prefill_traffic.json"
     if tp_.exists() and a.model == "llama3-8b" and a.gpus == 1:
         tj = json.loads(tp_.read_text())     # dram__bytes_read+write per launch from the committed ncu capture
         traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
