@@ -47,3 +47,15 @@ def test_tp2_fp8_and_mixtral_families(family, eager):
                                 B200_TP_ONESHOT_MAX_BYTES=os.environ.get("TP_TEST_ONESHOT_MAX_BYTES", str(8 << 20))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout
+
+
+def test_tp2_speculative_decoding_and_host_kv_tier():
+    """The speculative verification step (per-chunk sample COUNTS in the prefill broadcast) and the extended
+    KV cache's swap list (`_KIND_SWAP`) replayed by a second rank: outputs still follow the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_port()), str(ROOT / "tests" / "tp_parity_main.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TP_EAGER="0", TP_FEATURES="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "TP_PARITY" in r.stdout and '"ok": true' in r.stdout and '"features"' in r.stdout

@@ -36,15 +36,23 @@ def main():
                        num_local_experts=c.num_local_experts, num_experts_per_tok=c.num_experts_per_tok,
                        architecture="MixtralForCausalLM" if c.num_local_experts else "LlamaForCausalLM")
     weights = O.init_weights(c, seed=21)
-    ecfg = EngineConfig(tensor_parallel_size=world, max_num_seqs=8, max_num_batched_tokens=128, num_gpu_blocks=128,
+    features = os.environ.get("TP_FEATURES", "0") == "1"     # speculative decoding + host KV tier under TP
+    extra = {}
+    if features:
+        extra = dict(speculative_config={"method": "ngram", "num_speculative_tokens": 3, "prompt_lookup_max": 3,
+                                         "prompt_lookup_min": 1}, kv_host_cache_gib=1.0 / 64, enable_prefix_caching=True)
+    ecfg = EngineConfig(tensor_parallel_size=world, max_num_seqs=8, max_num_batched_tokens=128,
+                        num_gpu_blocks=40 if features else 128,
                         cuda_graph_sizes=[1, 2, 4, 8], enforce_eager=os.environ.get("TP_EAGER", "0") == "1",
-                        quantization="fp8" if family == "fp8" else None)
+                        quantization="fp8" if family == "fp8" else None, **extra)
     eng = LLMEngine.from_engine_config(ecfg, mcfg=mcfg, state_dict={k: v.cuda() for k, v in weights.items()})
     if rank != 0:
         TPWorker(eng).serve_forever()
         return
     g = torch.Generator().manual_seed(4)
     prompts = [torch.randint(3, c.vocab_size, (n,), generator=g).tolist() for n in (9, 40, 77, 130)]
+    if features:
+        prompts[1] = (prompts[1][:5] * 8)[:40]          # repetitive: the n-gram proposer drafts from the first step on
     oracle = O.OracleLlama(c, weights, quantization=ecfg.quantization)
     res = {"world": world, "family": family, "ok": True, "checks": []}
     outs = eng.generate(prompts, SamplingParams(max_tokens=12, ignore_eos=True))
@@ -60,6 +68,29 @@ def main():
             logits = oracle.forward(i, [o[t]])[-1]
         res["checks"].append({"seq": i, "checked": n_chk, "agree": n_ok})
         if n_ok != n_chk or n_chk < (3 if family == "dense" else 1):
+            res["ok"] = False
+    if features:
+        # a second batch evicts the first batch's cached blocks into the host tier; the first batch, asked again,
+        # is served from host memory (swap lists replayed by every rank) and must produce oracle-consistent tokens
+        others = [torch.randint(3, c.vocab_size, (n,), generator=g).tolist() for n in (150, 160, 140)]
+        eng.generate(others, SamplingParams(max_tokens=4, ignore_eos=True))
+        again = eng.generate(prompts, SamplingParams(max_tokens=12, ignore_eos=True))
+        n_ok = n_chk = 0
+        for i, (p, o) in enumerate(zip(prompts, again)):
+            oracle.reset()
+            logits = oracle.forward(i, p)[-1]
+            for t in range(len(o)):
+                top2 = torch.topk(logits, 2).values
+                if float(top2[0] - top2[1]) > tol * float(logits.abs().max()):
+                    n_chk += 1
+                    n_ok += int(int(torch.argmax(logits)) == o[t])
+                logits = oracle.forward(i, [o[t]])[-1]
+        st = eng.sched.spec_stats
+        res["features"] = {"spec_steps": st["steps"], "drafted": st["drafted"], "accepted": st["accepted"],
+                           "host_stored": eng.sched.pool.host_stored, "host_hit_tokens": eng.sched.pool.host_hits,
+                           "swap_in_blocks": eng.runner.stats.get("kv_swap_in_blocks", 0),
+                           "again_checked": n_chk, "again_agree": n_ok}
+        if not (st["steps"] > 0 and st["drafted"] > 0 and eng.sched.pool.host_hits > 0 and n_ok == n_chk and n_chk >= 8):
             res["ok"] = False
     # sampled requests across vocab shards: the in-kernel Gumbel-max draw is keyed by (seed, position,
     # GLOBAL vocab index), so a seed reproduces its tokens, another seed does not, and nucleus rows
