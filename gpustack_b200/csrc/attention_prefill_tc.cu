@@ -3,11 +3,11 @@
 // $VLLM/v1/attention/backends/flashinfer.py:1095-1230; on cc 10.x the reference engine runs
 // FlashInfer's TRT-LLM-gen FMHA cubins for this step).
 //
-// One CTA = one 128-row query tile of one (sequence, kv-head): the G = Hq/Hkv query heads that share
-// the kv-head times 128/G consecutive query tokens, so that S = Q K^T is a single UMMA M = 128 tile
-// and every K/V byte staged in shared memory serves the whole GQA group.
+// One work item = one 128-row query tile of one (sequence, kv-head): the G = Hq/Hkv query heads that
+// share the kv-head times 128/G consecutive query tokens, so that S = Q K^T is a single UMMA M = 128
+// tile and every K/V byte staged in shared memory serves the whole GQA group.
 //
-//   warp 4    TMA producer: the Q tile once, then K_j / V_j blocks of 64 tokens (4 KV pages of 16
+//   warp 4    TMA producer: the Q tile once per work item, then K_j / V_j blocks of 64 tokens (4 KV pages of 16
 //             tokens, each page two 2 KB boxes of the 128-byte-swizzled layout) through a 4-slot
 //             mbarrier ring; pages past the end of the sequence are read from the all-zero null block;
 //   warp 5    MMA issuer (one elected thread): S_j = Q K_j^T into one of two 64-column TMEM buffers,
@@ -17,15 +17,16 @@
 //             online softmax in base 2 with LAZY rescaling (the running reference maximum is only
 //             moved when the row maximum grows by more than 2^8, so the O accumulator in TMEM is
 //             rescaled rarely; P values stay <= 256, exact in fp32 / fine in bf16), P rounded to bf16
-//             into swizzled shared memory as the K-major A operand of the PV MMA; at the end
-//             O / l -> bf16 -> global.
+//             and written back over the S buffer's tensor-memory columns, from where the PV MMA reads
+//             it as its A operand (P_TMEM; the shared-memory route is kept for A/B runs); at the end
+//             O / l -> bf16 -> global.  The hand-off to the MMA warp is one mbarrier PER S BUFFER.
 //
 // V is consumed as an MN-major B operand straight from its [token][d] page layout (no transpose).
 // Two CTAs share an SM (112 KB of shared memory, 256 TMEM columns each): one CTA's softmax / epilogue
 // overlaps the other's MMAs.  Work per launch: 4 * T * ctx/2 * Hq * D FLOP (tensor-bound).
 //
-// PERSISTENT tile loop: the grid is 2 CTAs per SM and CTA c walks the work items c, c + grid, ...
-// of the (heaviest-first) list of (tile, kv-head) pairs.  Barriers, tensor memory and the K/V ring
+// PERSISTENT tile loop: the grid is 2 CTAs per SM and CTA c walks the (heaviest-first) list of
+// (tile, kv-head) work items in a boustrophedon static schedule (see work_of below).  Barriers, tensor memory and the K/V ring
 // live for the whole kernel; all mbarrier phases are running counters.  While a tile finishes (last
 // softmax block, PV, epilogue) the producer is already streaming the next tile's K/V into the ring
 // and -- once the last QK^T of the tile has retired (q_empty) -- its Q; every role loads the NEXT
