@@ -86,7 +86,8 @@ def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_l
     async def tokenize(req: Request):
         body = await req.json()
         ids = tokenizer.encode(body.get("prompt", ""))
-        return {"tokens": ids, "count": len(ids), "max_model_len": max_model_len}
+        return {"tokens": ids, "count": len(ids), "max_model_len": max_model_len,
+                "vocab_size": getattr(tokenizer, "vocab_size", None)}
 
     # ------------------------------------------------------------------ generation
     async def _parse(req: Request):

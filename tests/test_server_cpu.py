@@ -401,3 +401,53 @@ def test_round_robin_relay_alternates_between_two_replicas_and_streams():
             f.join(timeout=10)
         for th in threads:
             th.join(timeout=10)
+
+
+def test_benchmark_runner_accepts_gpustacks_command_line(tmp_path):
+    """tools/benchmark_runner.py is launched with the argv gpustack/worker/benchmark/runner.py:208-276 composes for
+    its runner container (Random dataset, constant rate, seed) and writes the result file into --output-dir."""
+    import socket
+    import subprocess
+    import sys
+    import threading
+    import types
+    import urllib.request
+    from pathlib import Path
+
+    from gpustack_b200.frontend import spawn_frontend
+
+    eng = StubEngine()
+    eng.mcfg = types.SimpleNamespace(vocab_size=600, bos_token_id=1, eos_token_id=2)
+    eng.ecfg = types.SimpleNamespace(max_model_len=512)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    front, core = spawn_frontend(eng, "127.0.0.1", port, "stub-model", None, "error")
+    th = threading.Thread(target=core.run, daemon=True)
+    th.start()
+    try:
+        url = f"http://127.0.0.1:{port}"
+        for _ in range(300):
+            try:
+                if urllib.request.urlopen(url + "/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.1)
+        root = Path(__file__).resolve().parents[1]
+        argv = ["benchmark", "run", "--target", url + "/v1", "--profile", "constant", "--rate", "20", "--sample-requests", "0",
+                "--processor", "/models/none", "--output-dir", str(tmp_path), "--outputs", "17.dual_json",
+                "--progress-url", "http://127.0.0.1:1/unused", "--progress-auth", "key",
+                "--backend-kwargs", json.dumps({"timeout": 600, "response_handlers": {"chat_completions": "x"}}),
+                "--backend", "openai_http_error_detail", "--data", "prompt_tokens=40,output_tokens=9",
+                "--random-seed", "42", "--max-requests", "10"]
+        r = subprocess.run([sys.executable, str(root / "tools" / "benchmark_runner.py")] + argv, capture_output=True,
+                           text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out = json.loads((tmp_path / "17.json").read_text())
+        m = out["metrics"]
+        assert m["successful"] == 10 and m["completion_tokens"] == 90 and m["prompt_tokens"] == 400
+        assert out["args"]["rate"] == 20.0 and out["model"] == "stub-model" and m["total_time_s"] >= 0.4   # 10 requests at 20 req/s
+    finally:
+        front.terminate()
+        front.join(timeout=10)
+        th.join(timeout=10)
