@@ -40,11 +40,19 @@ def main():
         span = torch.randint(300, 30000, (32,), generator=g).tolist()
         prompts.append((span * (a.input_len // 32 + 1))[: a.input_len])      # a repeated span: drafts from step one
     sp = SamplingParams(max_tokens=a.output_len, ignore_eos=True)
-    for spec in (None, {"method": "ngram", "num_speculative_tokens": a.k, "prompt_lookup_max": 4, "prompt_lookup_min": 2}):
+    cfg = {"method": "ngram", "num_speculative_tokens": a.k, "prompt_lookup_max": 4, "prompt_lookup_min": 2}
+    truth = {}
+    # plain decoding; the real proposer; then the two bounds of the method on this hardware: every draft wrong
+    # (pure cost of k+1-token verification steps) and every draft right (drafts = the plain run's own tokens)
+    for mode, spec in (("plain", None), ("ngram", cfg), ("all-drafts-wrong", cfg), ("all-drafts-right", cfg)):
         ecfg = EngineConfig(model=f"random:{a.model}", max_model_len=2048, max_num_seqs=16, max_num_batched_tokens=2048,
                             num_gpu_blocks=4096, enable_prefix_caching=False, speculative_config=spec)
         eng = make_engine(ecfg)
         eng.generate(prompts[:1], SamplingParams(max_tokens=8, ignore_eos=True))          # warm-up
+        if mode == "all-drafts-wrong":
+            eng.sched.proposer = lambda r, k: [7] * k
+        elif mode == "all-drafts-right":
+            eng.sched.proposer = lambda r, k: truth[tuple(r.prompt_ids)][len(r.output_ids):len(r.output_ids) + k]
         for c in cs:
             torch.cuda.synchronize()
             st0 = dict(eng.sched.spec_stats)
@@ -54,7 +62,9 @@ def main():
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             st = eng.sched.spec_stats
-            print(json.dumps({"model": a.model, "concurrency": c, "mode": "ngram" if spec else "plain",
+            if mode == "plain":
+                truth.update({tuple(p): o for p, o in zip(prompts[:c], outs)})
+            print(json.dumps({"model": a.model, "concurrency": c, "mode": mode,
                               "input_len": a.input_len, "output_len": a.output_len, "seconds": round(dt, 4),
                               "output_tok_s": round(c * a.output_len / dt, 1), "engine_steps": eng.counters["steps"] - steps0,
                               "tokens_per_step_per_seq": round(a.output_len / max(1, eng.counters["steps"] - steps0), 3),
