@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from gpustack_b200.kv_cache import BlockPool, KVCacheManager
-from gpustack_b200.scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler
+from gpustack_b200.scheduler import DecodePlan, MixedPlan, PrefillPlan, Request, SamplingParams, Scheduler, SpecPlan
+from gpustack_b200.spec_decode import SpeculativeConfig
 
 
 def mk(num_blocks=64, max_seqs=8, budget=64, max_len=256, eos=2):
@@ -381,17 +382,40 @@ from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E
 
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(seed=st.integers(0, 10_000), num_blocks=st.integers(12, 40), max_seqs=st.integers(1, 6),
-       budget=st.sampled_from([16, 48, 64, 200]), caching=st.booleans(), abort_p=st.floats(0.0, 0.2))
-def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budget, caching, abort_p):
+       budget=st.sampled_from([16, 48, 64, 200]), caching=st.booleans(), abort_p=st.floats(0.0, 0.2),
+       spec_k=st.sampled_from([0, 0, 2, 4]), host_slots=st.sampled_from([0, 0, 3, 40]))
+def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budget, caching, abort_p, spec_k, host_slots):
     """Random arrivals / aborts / EOS under KV pressure (forces chunking and preemption): every step
     respects the token and sequence budgets, chunks continue exactly where the request stopped, block
     tables of resident rows mirror the requests' block lists, no block is owned twice unless it is a
     shared (cached, full, read-only) prefix block, and everything is returned at the end."""
     rng = np.random.RandomState(seed)
     BS, max_len = 16, 160
-    s = Scheduler(num_blocks, BS, max_seqs, budget, max_len, 2, enable_prefix_caching=caching)
+    # speculative decoding (random drafts, randomly right) and the host KV tier ride along in some examples: the
+    # same budgets / ownership / leak invariants must hold with verification steps and swap lists in the mix
+    spec = SpeculativeConfig(num_speculative_tokens=spec_k) if spec_k else None
+    s = Scheduler(num_blocks, BS, max_seqs, budget, max_len, 2, enable_prefix_caching=caching, speculative=spec,
+                  max_sample_rows=max_seqs * (1 + spec_k), kv_host_slots=host_slots)
+    if spec:
+        s.proposer = lambda r, k: rng.choice([7, 9], size=int(rng.randint(0, k + 1))).tolist()
     heads = [rng.randint(3, 300, size=n).tolist() for n in (16, 40)]
     live, nreq, steps, finished, mixed_seen = {}, 0, 0, 0, 0
+
+    def check_ownership():
+        # ownership: a block has several owners only if it is a cached full block inside every owner's computed prefix
+        owners = {}
+        for r in list(s.prefilling) + [x for x in s.rows if x is not None]:
+            assert not r.finished
+            for j, b in enumerate(r.blocks):
+                assert 0 < b < num_blocks
+                owners.setdefault(b, []).append((r, j))
+        for b, lst in owners.items():
+            assert s.pool._ref[b] == len(lst) and b not in s.pool._free
+            if len(lst) > 1:
+                assert caching and s.pool._key[b] is not None
+                assert len({j for _, j in lst}) == 1                        # same logical position in every owner
+        assert len(s.pool._free) + len(owners) == num_blocks - 1
+
     while steps < 600:
         steps += 1
         if nreq < 25 and rng.rand() < 0.4:
@@ -410,9 +434,31 @@ def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budg
                 assert s.abort(rid)
                 assert live[rid].finished and live[rid].finish_reason == "abort" and not live[rid].blocks
         plan = s.schedule()
+        for kind, blk, slot in s.pool.take_swap_ops():          # host tier: well-formed operations only
+            assert kind in (0, 1) and 0 < blk < num_blocks and 0 <= slot < host_slots
         if plan is None:
             if nreq >= 25 and not s.has_work():
                 break
+            continue
+        if isinstance(plan, SpecPlan):
+            B = plan.batch
+            assert B == len(s.rows) and len(plan.drafts) == B and any(plan.drafts)
+            assert plan.num_tokens <= budget and plan.num_tokens <= s.max_sample_rows
+            sampled = []
+            for i, r in enumerate(s.rows):
+                d = plan.drafts[i]
+                assert len(d) <= spec_k and len(d) <= r.params.max_tokens - len(r.output_ids) - 1
+                assert (int(s.num_computed[i]) + len(d)) // BS < len(r.blocks)          # K/V slots for every draft
+                assert int(s.n_blocks[i]) == len(r.blocks) and s.block_table[i, : len(r.blocks)].tolist() == r.blocks
+                # the "model": agrees with a draft with probability 1/2, otherwise says 2 (EOS), 7 or 9
+                sampled += [int(t) if rng.rand() < 0.5 else int(rng.choice([2, 7, 9])) for t in d] + [int(rng.choice([7, 9]))]
+            before = {r.req_id: len(r.output_ids) for r in s.rows}
+            out = s.update_spec(plan, sampled)
+            finished += sum(f is not None for f in out.finished)
+            for rid in set(out.req_ids):
+                emitted = out.req_ids.count(rid)
+                assert 1 <= emitted <= spec_k + 1 and len(live[rid].output_ids) == before[rid] + emitted
+            check_ownership()
             continue
         pre = plan.prefill if isinstance(plan, MixedPlan) else plan if isinstance(plan, PrefillPlan) else None
         B = 0 if isinstance(plan, PrefillPlan) else plan.batch
@@ -445,19 +491,7 @@ def test_scheduler_invariants_under_random_load(seed, num_blocks, max_seqs, budg
         else:
             out = s.update_decode(plan, dtoks)
         finished += sum(f is not None for f in out.finished)
-        # ownership: a block has several owners only if it is a cached full block inside every owner's computed prefix
-        owners = {}
-        for r in list(s.prefilling) + [x for x in s.rows if x is not None]:
-            assert not r.finished
-            for j, b in enumerate(r.blocks):
-                assert 0 < b < num_blocks
-                owners.setdefault(b, []).append((r, j))
-        for b, lst in owners.items():
-            assert s.pool._ref[b] == len(lst) and b not in s.pool._free
-            if len(lst) > 1:
-                assert caching and s.pool._key[b] is not None
-                assert len({j for _, j in lst}) == 1                        # same logical position in every owner
-        assert len(s.pool._free) + len(owners) == num_blocks - 1
+        check_ownership()
     assert not s.has_work() or steps >= 600
     if not s.has_work():
         assert s.pool.num_free == s.pool.num_total
