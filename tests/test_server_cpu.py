@@ -451,3 +451,68 @@ def test_benchmark_runner_accepts_gpustacks_command_line(tmp_path):
         front.terminate()
         front.join(timeout=10)
         th.join(timeout=10)
+
+
+def test_streams_stay_ordered_when_a_step_emits_several_tokens_per_request():
+    """Speculative decoding makes one engine step emit up to k+1 tokens for the same request: the step output then
+    carries the request id several times.  Text, order, finish reason and usage must come out as with one token
+    per step."""
+    from gpustack_b200.scheduler import SpecPlan
+    from gpustack_b200.spec_decode import SpeculativeConfig
+
+    class SpecStub(StubEngine):
+        def __init__(self):
+            super().__init__()
+            self.sched = Scheduler(256, 16, 8, 128, 512, eos_token_id=2,
+                                   speculative=SpeculativeConfig(num_speculative_tokens=3), max_sample_rows=32)
+            # drafts = the sentence's true continuation: always accepted
+            self.sched.proposer = lambda r, k: [self.ids[(len(r.output_ids) + j) % len(self.ids)] for j in range(k)]
+            self.multi = 0
+
+        def step(self):
+            plan = self.sched.schedule()
+            if isinstance(plan, SpecPlan):
+                sampled = []
+                for i in range(plan.batch):
+                    r = self.sched.rows[i]
+                    n0 = len(r.output_ids)
+                    sampled += [self.ids[(n0 + j) % len(self.ids)] for j in range(1 + len(plan.drafts[i]))]
+                out = self.sched.update_spec(plan, sampled)
+                self.multi += int(len(out.req_ids) > len(set(out.req_ids)))
+                self.counters["generation_tokens"] += len(out.token_ids)
+                return out
+            if plan is None:
+                return None
+            # not a spec plan: replay StubEngine.step on the plan that was already scheduled
+            if isinstance(plan, MixedPlan):
+                pre = [self._next(r) for r, s in zip(plan.prefill.reqs, plan.prefill.sample) if s]
+                dec = np.array([self._next(r) for r in self.sched.rows[:plan.batch]], dtype=np.int32)
+                out = self.sched.update_mixed(plan, pre, dec)
+            elif isinstance(plan, PrefillPlan):
+                out = self.sched.update_prefill(plan, [self._next(r) for r, s in zip(plan.reqs, plan.sample) if s])
+            else:
+                out = self.sched.update_decode(plan, np.array([self._next(r) for r in self.sched.rows], dtype=np.int32))
+            self.counters["generation_tokens"] += len(out.token_ids)
+            return out
+
+    eng = SpecStub()
+    aeng = AsyncEngine(eng)
+    app = create_app(aeng, eng.tok, "stub-model", 512)
+    try:
+        with TestClient(app) as c:
+            with c.stream("POST", "/v1/chat/completions", json={
+                    "model": "stub-model", "messages": [{"role": "user", "content": "hi"}], "max_tokens": 41,
+                    "stream": True, "temperature": 0, "ignore_eos": True, "stream_options": {"include_usage": True}}) as resp:
+                events = _sse(resp)
+            chunks = [ChatCompletionChunk.model_validate_json(e) for e in events[:-1]]
+            text = "".join(ch.choices[0].delta.content or "" for ch in chunks if ch.choices)
+            assert text == (StubEngine.TEXT * 3)[:41]
+            assert [ch.choices[0].finish_reason for ch in chunks if ch.choices][-1] == "length"
+            assert chunks[-1].usage.completion_tokens == 41
+            # non-streaming, same engine: several requests at once
+            r = c.post("/v1/completions", json={"model": "stub-model", "prompt": "abc", "max_tokens": 30, "temperature": 0,
+                                                "ignore_eos": True})
+            assert r.json()["choices"][0]["text"] == (StubEngine.TEXT * 3)[:30] and r.json()["usage"]["completion_tokens"] == 30
+        assert eng.multi > 0 and eng.sched.spec_stats["accepted"] > 0
+    finally:
+        aeng._stop = True
