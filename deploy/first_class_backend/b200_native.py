@@ -15,8 +15,12 @@ What the first-class path adds over the custom-backend YAML (deploy/inference-ba
   * the engine's EXACT VRAM requirement as the resource claim (gpustack_b200.resource_fit: weights
     per dtype + workspace + CUDA-graph pool + the KV capacity asked for) instead of the
     `weights x 1.2 + 2 GiB` heuristic of CustomBackendResourceFitSelector
-    (gpustack/policies/utils.py:283-360).
+    (gpustack/policies/utils.py:283-360);
+  * the model's `speculative_config` (n-gram method) and `extended_kv_cache` turned into the engine's
+    `--speculative-config` / `--kv-host-cache-gib` flags, which the built-in vLLM backend does for its own engine
+    (vllm.py:256-275,333-367,468-483) and a custom backend cannot (it only sees backend_parameters).
 """
+import json
 from typing import List
 
 from gpustack.policies.candidate_selectors.custom_backend_resource_fit_selector import (
@@ -42,12 +46,44 @@ class B200NativeServer(CustomServer):
         # single worker, several GPUs -> --tensor-parallel-size len(gpu_indexes); multi-worker is not
         # supported by this engine (one NVSwitch node), so is_distributed is always False
         args += get_auto_parallelism_arguments(self._model.backend_parameters, self._model_instance, False)
+        args += self._speculative_arguments() + self._extended_kv_arguments()
         args += self._flatten_backend_param()                    # base.py:867-891
         for flag, value in (("--host", self._worker.ip), ("--port", str(port)),
                             ("--served-model-name", self._model.name)):
             if find_parameter(args, [flag.lstrip("-")]) is None:
                 args += [flag, value]
         return args
+
+
+    def _speculative_arguments(self) -> List[str]:
+        """Model.speculative_config -> --speculative-config JSON (the field names the vLLM launcher uses, so the
+        engine's parser is the same for both registration routes).  Only the n-gram method has an implementation
+        in the engine; eagle3 / mtp models are launched without speculation (the engine would warn and ignore)."""
+        sc = getattr(self._model, "speculative_config", None)
+        if not sc or not sc.enabled or str(getattr(sc.algorithm, "value", sc.algorithm)).lower() != "ngram":
+            return []
+        cfg = {"method": "ngram"}
+        if sc.num_draft_tokens:
+            cfg["num_speculative_tokens"] = sc.num_draft_tokens
+        if sc.ngram_max_match_length:
+            cfg["prompt_lookup_max"] = sc.ngram_max_match_length
+        if sc.ngram_min_match_length:
+            cfg["prompt_lookup_min"] = sc.ngram_min_match_length
+        return ["--speculative-config", json.dumps(cfg)]
+
+    def _extended_kv_arguments(self) -> List[str]:
+        """Model.extended_kv_cache -> the host-memory tier of the prefix cache, sized like the reference sizes
+        LMCache: explicit ram_size (GiB), else ram_ratio x the VRAM claim."""
+        kv = getattr(self._model, "extended_kv_cache", None)
+        if not kv or not kv.enabled:
+            return []
+        if kv.ram_size and kv.ram_size > 0:
+            gib = float(kv.ram_size)
+        else:
+            claim = sum((self._model_instance.computed_resource_claim.vram or {}).values()) if \
+                self._model_instance.computed_resource_claim else 0
+            gib = claim * float(kv.ram_ratio or 1.2) / (1 << 30)
+        return ["--kv-host-cache-gib", f"{gib:.2f}"] if gib > 0 else []
 
 
 class B200NativeResourceFitSelector(CustomBackendResourceFitSelector):
