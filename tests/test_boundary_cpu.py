@@ -88,3 +88,89 @@ def test_first_class_backend_binding_compiles():
 
     est = estimate(tiny_llama(), EngineConfig(tensor_parallel_size=2))
     assert est.total_min == est.per_gpu_min * 2 and est.total_min > 0
+
+
+def test_first_class_backend_binding_builds_the_engine_argv_under_stand_in_gpustack_modules():
+    """The binding imports gpustack.* (not installable offline).  With stand-ins for exactly the four names it
+    imports -- behaving as the reference documents them -- `_build_command_args` must compose the argv our CLI parses:
+    TP from the GPU count, max-model-len capping, speculative / extended-KV model fields as engine flags, user
+    parameters, host / port / served name.  The argv is then fed to the real `b200-engine` parser."""
+    import importlib.util
+    import json
+    import sys
+    import types
+
+    from tests import gpustack_compat as G
+
+    mods = {}
+
+    def mod(name):
+        m = types.ModuleType(name)
+        mods[name] = m
+        return m
+
+    for pkg in ("gpustack", "gpustack.policies", "gpustack.policies.candidate_selectors", "gpustack.utils",
+                "gpustack.worker", "gpustack.worker.backends"):
+        mod(pkg).__path__ = []
+    mod("gpustack.policies.candidate_selectors.custom_backend_resource_fit_selector").CustomBackendResourceFitSelector = object
+    mod("gpustack.utils.command").find_parameter = G.find_parameter
+
+    class CustomServer:                                   # the members the binding relies on (custom.py / base.py)
+        def _get_serving_port(self):
+            return 40123
+
+        def build_versioned_command_args(self, args):
+            return list(args)
+
+        def _derive_max_model_len(self):
+            return 131072
+
+        def _flatten_backend_param(self):
+            return G.flatten_backend_param(self._model.backend_parameters)
+
+    mod("gpustack.worker.backends.custom").CustomServer = CustomServer
+    mod("gpustack.worker.backends.vllm").get_auto_parallelism_arguments = (
+        lambda params, inst, dist: [] if G.find_parameter(params, ["tensor-parallel-size", "tp"]) else
+        ["--tensor-parallel-size", str(len(inst.gpu_indexes))])
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    try:
+        spec = importlib.util.spec_from_file_location("b200_native_binding",
+                                                      ROOT / "deploy" / "first_class_backend" / "b200_native.py")
+        binding = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(binding)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    srv = binding.B200NativeServer.__new__(binding.B200NativeServer)
+    ns = types.SimpleNamespace
+    srv._model_path = "/models/llama3-8b"
+    srv._worker = ns(ip="10.0.0.5")
+    srv._model = ns(name="llama3-8b", backend_parameters=["--max-num-seqs 128", "--enable-prefix-caching"],
+                    speculative_config=ns(enabled=True, algorithm=ns(value="ngram"), num_draft_tokens=3,
+                                          ngram_max_match_length=4, ngram_min_match_length=2, draft_model=None),
+                    extended_kv_cache=ns(enabled=True, ram_size=None, ram_ratio=0.5, chunk_size=None))
+    srv._model_instance = ns(gpu_indexes=[0, 1, 2, 3], computed_resource_claim=ns(vram={i: 40 << 30 for i in range(4)}))
+    argv = srv._build_command_args()
+    assert argv[:2] == ["serve", "/models/llama3-8b"]
+    from gpustack_b200.cli import _engine_config, build_parser
+
+    a = build_parser().parse_args(argv)
+    assert (a.tensor_parallel_size, a.max_model_len, a.max_num_seqs, a.host, a.port) == ("4", 8192, 128, "10.0.0.5", 40123)
+    assert a.served_model_name == ["llama3-8b"]
+    e = _engine_config(a, 4)
+    assert e.speculative().num_speculative_tokens == 3 and e.speculative().prompt_lookup_max == 4
+    assert abs(e.kv_host_cache_gib - 80.0) < 1e-6                  # 0.5 x (4 x 40 GiB)
+    assert json.loads(a.speculative_config)["method"] == "ngram"
+    # an eagle3 model: launched without speculation instead of failing the deployment
+    srv._model.speculative_config = ns(enabled=True, algorithm=ns(value="eagle3"), num_draft_tokens=2,
+                                       ngram_max_match_length=None, ngram_min_match_length=None, draft_model="d")
+    srv._model.extended_kv_cache = ns(enabled=False, ram_size=None, ram_ratio=1.2, chunk_size=None)
+    srv._model.backend_parameters = ["--max-model-len=4096", "--tensor-parallel-size 2"]
+    argv = srv._build_command_args()
+    a = build_parser().parse_args(argv)
+    assert a.speculative_config is None and a.kv_host_cache_gib is None and a.max_model_len == 4096
+    assert a.tensor_parallel_size == "2" and argv.count("--tensor-parallel-size") == 1
