@@ -90,7 +90,7 @@ def test_first_class_backend_binding_compiles():
     assert est.total_min == est.per_gpu_min * 2 and est.total_min > 0
 
 
-def test_first_class_backend_binding_builds_the_engine_argv_under_stand_in_gpustack_modules():
+def test_first_class_backend_binding_builds_the_engine_argv_under_stand_in_gpustack_modules(tmp_path):
     """The binding imports gpustack.* (not installable offline).  With stand-ins for exactly the four names it
     imports -- behaving as the reference documents them -- `_build_command_args` must compose the argv our CLI parses:
     TP from the GPU count, max-model-len capping, speculative / extended-KV model fields as engine flags, user
@@ -174,3 +174,17 @@ def test_first_class_backend_binding_builds_the_engine_argv_under_stand_in_gpust
     a = build_parser().parse_args(argv)
     assert a.speculative_config is None and a.kv_host_cache_gib is None and a.max_model_len == 4096
     assert a.tensor_parallel_size == "2" and argv.count("--tensor-parallel-size") == 1
+    # the selector's claim = the engine's own VRAM model for the scheduled GPU count
+    from gpustack_b200.config import EngineConfig, llama3_8b
+    from gpustack_b200.resource_fit import estimate
+
+    d = tmp_path / "llama3-8b"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps(llama3_8b().to_hf_dict()))
+    sel = binding.B200NativeResourceFitSelector.__new__(binding.B200NativeResourceFitSelector)
+    sel._gpu_count = 2
+    sel._model = ns(local_path=str(d), backend_parameters=["--max-model-len 8192"])
+    sel._model_path = str(d)
+    sel._set_vram_claim()
+    want = estimate(llama3_8b(), EngineConfig(tensor_parallel_size=2, max_model_len=8192)).total_min
+    assert sel._vram_claim == want and 16e9 < want < 40e9          # 16 GB of weights + workspace + one 8k sequence of KV
