@@ -57,6 +57,8 @@ def build_parser() -> argparse.ArgumentParser:
                         'the env the launcher sets; default 5)')
     s.add_argument("--kv-host-cache-gib", type=float, default=None,
                    help="host-memory tier of the prefix cache in GiB (native spelling of the above)")
+    s.add_argument("--stream-interval", type=int, default=1,
+                   help="engine outputs per SSE chunk (first and last outputs of a request are never held back)")
     s.add_argument("--dtype", default="bfloat16")
     s.add_argument("--log-level", default="info")
     est = sub.add_parser("estimate", help="print the engine's exact VRAM requirement (GPUSTACK_MODEL_VRAM_CLAIM)")
@@ -185,7 +187,8 @@ def main(argv: Optional[List[str]] = None) -> int:
         name = ecfg.served_model_name or os.path.basename(os.path.normpath(args.model))
         model_path = None if args.model.startswith("random:") else args.model
         # this (GPU-owning) process runs the engine-core busy loop; HTTP lives in a child process
-        front, core = spawn_frontend(eng, args.host, args.port, name, model_path, args.log_level)
+        front, core = spawn_frontend(eng, args.host, args.port, name, model_path, args.log_level,
+                                     stream_interval=max(1, args.stream_interval))
         log.info("serving %s on %s:%d (tp=%d, %d KV blocks, max_model_len=%d)", name, args.host, args.port, tp,
                  eng.num_blocks, ecfg.max_model_len)
         try:

@@ -51,7 +51,11 @@ def _sampling(body: Dict[str, Any], max_model_len: int, prompt_len: int, tokeniz
                           stop_token_ids=stop_ids, seed=body.get("seed"))
 
 
-def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_len: int) -> FastAPI:
+def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_len: int,
+               stream_interval: int = 1) -> FastAPI:
+    """stream_interval: engine outputs folded into one SSE chunk (the reference engine's `--stream-interval`): 1 =
+    a chunk per output, N = a chunk every N outputs; the first output (TTFT) and the last (finish_reason) are
+    always sent at once."""
     app = FastAPI(title="b200-native engine", version=__version__)
     created = int(time.time())
 
@@ -176,7 +180,14 @@ def create_app(aeng: AsyncEngine, tokenizer, served_model_name: str, max_model_l
             async def sse():
                 n_out = 0
                 try:
+                    held, n_held = "", 0
                     async for delta, fin, first, n_out in events():
+                        if stream_interval > 1 and not first:
+                            held += delta
+                            n_held += 1
+                            if fin is None and n_held < stream_interval:
+                                continue
+                            delta, held, n_held = held, "", 0
                         if delta or fin is not None or first:
                             yield f"data: {_dumps(chunk(delta, fin, first))}\n\n"
                     if include_usage:

@@ -516,3 +516,24 @@ def test_streams_stay_ordered_when_a_step_emits_several_tokens_per_request():
         assert eng.multi > 0 and eng.sched.spec_stats["accepted"] > 0
     finally:
         aeng._stop = True
+
+
+def test_stream_interval_folds_outputs_but_never_the_first_or_the_last():
+    eng = StubEngine()
+    aeng = AsyncEngine(eng)
+    app = create_app(aeng, eng.tok, "stub-model", 512, stream_interval=5)
+    try:
+        with TestClient(app) as c:
+            with c.stream("POST", "/v1/chat/completions", json={
+                    "model": "stub-model", "messages": [{"role": "user", "content": "hi"}], "max_tokens": 23,
+                    "stream": True, "temperature": 0, "ignore_eos": True, "stream_options": {"include_usage": True}}) as resp:
+                events = _sse(resp)
+            chunks = [ChatCompletionChunk.model_validate_json(e) for e in events[:-1]]
+            body = [ch for ch in chunks if ch.choices]
+            assert "".join(ch.choices[0].delta.content or "" for ch in body) == StubEngine.TEXT[:23]
+            assert body[0].choices[0].delta.role == "assistant" and len(body[0].choices[0].delta.content) <= 2   # first output alone
+            assert body[-1].choices[0].finish_reason == "length" and all(ch.choices[0].finish_reason is None for ch in body[:-1])
+            assert len(body) <= 2 + (23 + 4) // 5 and max(len(ch.choices[0].delta.content or "") for ch in body[1:]) >= 4
+            assert chunks[-1].usage.completion_tokens == 23
+    finally:
+        aeng._stop = True
